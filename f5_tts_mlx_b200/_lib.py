@@ -1,0 +1,76 @@
+"""ctypes binding of libf5b200.so (the C ABI declared in include/f5_b200.h).
+
+There is no fallback: if the shared object is missing the import of any compute module raises, and
+if no sm_100 GPU is present every entry point returns F5_ERR_NO_DEVICE which `check()` turns into a
+RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libf5b200.so"
+_lib = None
+
+
+class F5Error(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise F5Error(
+                f"{_LIB_PATH} is missing: build it with `python -m f5_tts_mlx_b200.build` "
+                "(nvcc, sm_100a). This package has no CPU / PyTorch fallback."
+            )
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.f5_last_error.restype = C.c_char_p
+        _declare(_lib)
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = load().f5_last_error().decode("utf-8", "replace")
+        raise F5Error(f"libf5b200 error {code}: {msg}")
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_int64),
+        ("w", C.c_void_p), ("ldw", C.c_int64),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("rows_per_batch", C.c_int32), ("num_batches", C.c_int32), ("batched_tiles", C.c_int32),
+        ("conv_taps", C.c_int32), ("conv_pad", C.c_int32), ("conv_grouped", C.c_int32),
+        ("act", C.c_int32), ("out_bf16", C.c_int32),
+        ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int64),
+        ("row_len", C.c_void_p),
+        ("rope", C.c_void_p), ("rope_cols", C.c_int32),
+        ("q_scale", C.c_float), ("q_cols", C.c_int32),
+        ("tile_n", C.c_int32),
+    ]
+
+
+# exported symbols -> (restype, argtypes); tests check that every one of these resolves
+SYMBOLS: dict[str, tuple] = {
+    "f5_last_error": (C.c_char_p, []),
+    "f5_abi_version": (C.c_int, []),
+    "f5_device_check": (C.c_int, []),
+    "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+}
+
+
+def _declare(lib: C.CDLL) -> None:
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args

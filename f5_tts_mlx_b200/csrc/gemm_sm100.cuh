@@ -1,0 +1,287 @@
+// tcgen05 + TMA GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] (bf16, K-major) · W[N,K]^T (bf16) )
+//
+// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0     TMA producer   (one elected lane): A/B k-blocks -> 128B-swizzled smem ring
+//   warp 1     MMA issuer     (one elected lane): tcgen05.mma kind::f16, fp32 accumulator in TMEM
+//   warps 2-5  epilogue       (128 threads = 128 TMEM lanes = 128 output rows)
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and one tmem_full mbarrier (MMA -> epilogue).
+// With kStages*(16+BN/8) KB of smem two CTAs can be co-resident per SM, so one CTA's epilogue
+// overlaps the other's main loop (TMEM: 2 x BN columns <= 512).
+//
+// The same kernel runs the 1-D convolutions of the path as implicit GEMMs: the A operand is a
+// 3-D tensor map (channels, frames, batch) and k-block kb reads the tile shifted by
+// (tap - pad) frames; TMA zero-fills the out-of-range frames, which is exactly the conv's zero
+// padding (reference: nn.Conv1d(padding=k//2), dit.py:33-38).
+//
+// Epilogue (all fp32, fused, per reference op):
+//   v = acc + bias[col]                                   Linear bias        (dit.py:136-143 ...)
+//   v = act(v)            none | GELU-tanh | GELU-erf | Mish   (dit.py:94-99, convnext_v2.py:41, dit.py:36)
+//   RoPE on adjacent column pairs for col < rope_cols     (rope.py:87-107, dit.py:157-158)
+//   v *= q_scale for col < q_cols                         softmax scale folded into q (dit.py:166)
+//   v = row valid ? v : 0                                 "x * mask" (dit.py:172-173)
+//   v *= gate[batch, col]                                 AdaLN-Zero gate (dit.py:319,323)
+//   v += resid[row, col]                                  residual (fp32 stream)
+//   store fp32 or bf16
+#pragma once
+#include "ptx.cuh"
+
+namespace f5 {
+
+enum GemmAct { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_MISH = 3 };
+
+struct GemmParams {
+  int M, N, K;             // logical problem (flat mode: M rows; batched mode: see below)
+  // row mapping
+  int rows_per_batch;      // frames per utterance (row -> batch = row / rows_per_batch); 0 = M
+  int tiles_per_batch;     // >0: M tiles never straddle utterances (batched / conv mode)
+  int num_batches;
+  // implicit-conv mode
+  int conv_taps;           // 1 = plain GEMM
+  int conv_pad;            // frames of left padding (k//2)
+  int k_per_tap;           // K elements per tap (multiple of 64)
+  int conv_grouped;        // 1: A channel base = output column base (block-diagonal groups of 64)
+  // epilogue
+  const float* bias;       // [N] or null
+  void* out;               // bf16 or f32, row-major, ldo elements
+  int ldo;
+  const float* resid;      // f32 [rows, ldr] or null (may alias out)
+  int ldr;
+  const float* gate;       // f32 [num_batches, gate_ld] or null
+  int gate_ld;
+  const int* row_len;      // [num_batches] valid frames per utterance, or null
+  const float2* rope;      // [rows_per_batch, 32] (cos, sin), or null
+  int rope_cols;
+  float q_scale;
+  int q_cols;
+};
+
+template <int BN, int kStages>
+struct GemmSmem {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = BN * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;  // + align slack
+};
+
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
+                    const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  using S = GemmSmem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles must sit on 1024-byte boundaries
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates ----
+  const int n0 = blockIdx.x * BN;
+  int batch = 0, m_in_batch0 = 0, row0;
+  if (p.tiles_per_batch > 0) {
+    batch = blockIdx.y / p.tiles_per_batch;
+    m_in_batch0 = (blockIdx.y % p.tiles_per_batch) * 128;
+    row0 = batch * p.rows_per_batch + m_in_batch0;
+  } else {
+    row0 = blockIdx.y * 128;
+    m_in_batch0 = row0;
+  }
+  const int kb_per_tap = (p.k_per_tap + 63) >> 6;
+  const int num_kb = p.conv_taps * kb_per_tap;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        const int tap = kb / kb_per_tap;
+        const int kc = kb - tap * kb_per_tap;
+        const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
+        tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
+                    p.tiles_per_batch > 0 ? batch : 0);
+        tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) per 64-wide k-block; +32 B per step
+          uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+          uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+          umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);                        // frees the smem slot when MMAs retire
+        if (kb == num_kb - 1) tc_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int r_in_tile = lg * 32 + lane;
+    const int m_in_batch = m_in_batch0 + r_in_tile;
+    const int row = row0 + r_in_tile;
+    bool row_ok;
+    int b_idx, pos;
+    if (p.tiles_per_batch > 0) {
+      row_ok = m_in_batch < p.rows_per_batch;
+      b_idx = batch;
+      pos = m_in_batch;
+    } else {
+      row_ok = row < p.M;
+      const int rpb = p.rows_per_batch > 0 ? p.rows_per_batch : p.M;
+      b_idx = row / rpb;
+      pos = row - b_idx * rpb;
+    }
+    if (!row_ok) { b_idx = 0; pos = 0; }
+    bool row_valid = true;
+    if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, acc);
+      tmem_wait_ld();
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) continue;  // uniform per CTA
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + j < p.N) {
+            float4 bb = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+          }
+        }
+      }
+      if (ACT == ACT_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+      } else if (ACT == ACT_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+      } else if (ACT == ACT_MISH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = mish_f(v[j]);
+      }
+      if (ROPE) {
+        if (col0 < p.rope_cols) {
+          const float2* rp = p.rope + (size_t)pos * 32 + ((col0 & 63) >> 1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float2 cs = rp[j];
+            float a = v[2 * j], b = v[2 * j + 1];
+            v[2 * j] = a * cs.x - b * cs.y;
+            v[2 * j + 1] = b * cs.x + a * cs.y;
+          }
+        }
+        if (col0 < p.q_cols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.q_scale;
+        }
+      }
+      if (!row_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (p.gate != nullptr) {
+        const float* g = p.gate + (size_t)b_idx * p.gate_ld + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (col0 + j < p.N) {
+            float4 gg = *reinterpret_cast<const float4*>(g + j);
+            v[j] *= gg.x; v[j + 1] *= gg.y; v[j + 2] *= gg.z; v[j + 3] *= gg.w;
+          }
+        }
+      }
+      if (row_ok) {
+        if (p.resid != nullptr) {
+          const float* rr = p.resid + (size_t)row * p.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              float4 x = *reinterpret_cast<const float4*>(rr + j);
+              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+            }
+          }
+        }
+        if (OUT_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 w;
+              w.x = pack_bf16x2(v[j], v[j + 1]);
+              w.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              w.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              w.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = w;
+            }
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < p.N) {
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace f5

@@ -1,0 +1,39 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, device check,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/f5_b200.h"
+
+namespace f5 {
+
+int set_error(int code, const char* fmt, ...);
+
+#define F5_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return f5::set_error(F5_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+  } while (0)
+
+#define F5_REQUIRE(cond, ...)                                        \
+  do {                                                               \
+    if (!(cond)) return f5::set_error(F5_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+// 0 if an sm_100 device is current, else F5_ERR_NO_DEVICE (message set)
+int device_check();
+
+// bf16 tensor map with 128-byte swizzle and zero OOB fill.  dims/strides innermost first;
+// strides in BYTES for dims 1.. (rank-1 entries).  Returns 0 or error.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace f5
