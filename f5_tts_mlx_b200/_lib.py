@@ -57,6 +57,7 @@ class GemmArgs(C.Structure):
         ("rope", C.c_void_p), ("rope_cols", C.c_int32),
         ("q_scale", C.c_float), ("q_cols", C.c_int32),
         ("tile_n", C.c_int32),
+        ("out2_bf16", C.c_void_p), ("ldo2", C.c_int64),
     ]
 
 
@@ -66,6 +67,19 @@ SYMBOLS: dict[str, tuple] = {
     "f5_abi_version": (C.c_int, []),
     "f5_device_check": (C.c_int, []),
     "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "f5_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "f5_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "f5_dwconv7_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f5_grn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                         C.c_int32, C.c_void_p]),
+    "f5_dit_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f5_dit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "f5_ode_eval_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32]),
+    "f5_ode_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -1,0 +1,35 @@
+// Host launcher + C-ABI entry for the tcgen05 flash-attention forward (attention_sm100.cuh).
+#include "attention_sm100.cuh"
+#include "host_common.h"
+
+extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
+                                int32_t batch, int32_t frames, int32_t heads, int32_t head_dim,
+                                const int32_t* kv_len, void* stream_) {
+  using namespace f5;
+  if (int e = device_check()) return e;
+  F5_REQUIRE(qkv && out, "f5_attention_fwd: null pointer");
+  F5_REQUIRE(head_dim == 64, "f5_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
+  F5_REQUIRE(batch > 0 && frames > 0 && heads > 0, "f5_attention_fwd: bad shape");
+  F5_REQUIRE(ld_qkv % 8 == 0 && ld_qkv >= 3 * heads * 64, "f5_attention_fwd: bad ld_qkv");
+  F5_REQUIRE(ld_out % 8 == 0 && ld_out >= heads * 64, "f5_attention_fwd: bad ld_out");
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)3 * heads * 64, (uint64_t)frames, (uint64_t)batch};
+  uint64_t str[2] = {(uint64_t)ld_qkv * 2, (uint64_t)ld_qkv * 2 * (uint64_t)frames};
+  uint32_t box[3] = {64, 128, 1};
+  if (int e = make_tmap_bf16(&tm, qkv, 3, dims, str, box)) return e;
+  AttnParams p;
+  p.B = batch; p.N = frames; p.H = heads;
+  p.kv_len = kv_len;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = (int)ld_out;
+  static bool attr_set = false;
+  if (!attr_set) {
+    F5_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnSmem::kTotal));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(frames, 128), heads, batch);
+  attn_fwd_kernel<<<grid, 192, AttnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream_)>>>(tm, p);
+  F5_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

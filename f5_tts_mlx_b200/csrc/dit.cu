@@ -1,0 +1,273 @@
+// DiT forward and the ODE loop of F5TTS.sample as a stream-ordered sequence of the sm_100a kernels
+// in this directory (C-ABI: f5_dit_precompute / f5_dit_forward / f5_ode_sample).
+//
+// What the reference recomputes on every forward but depends only on (text, cond, t) is hoisted:
+//   * TextEmbedding (dit.py:390)                      -> once per sample, per CFG branch
+//   * cond·Wc + text·Wt + b of InputEmbedding.proj    -> once per sample (dit.py:249)
+//   * TimestepEmbedding + all 23 AdaLN linears         -> one GEMM over all time points (dit.py:389,267,286)
+// and the two unbatched CFG passes (cfm.py:342-363) run as one forward over a doubled batch.
+#include <string.h>
+
+#include "host_common.h"
+#include "launch.h"
+
+extern "C" int f5_attention_fwd(const void*, int64_t, void*, int64_t, int32_t, int32_t, int32_t,
+                                int32_t, const int32_t*, void*);
+
+namespace f5 {
+
+static f5_gemm_args gemm_base(const void* a, int64_t lda, const void* w, int64_t ldw, int m, int n,
+                              int k, void* out, int64_t ldo, bool out_bf16) {
+  f5_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = a; g.lda = lda; g.w = w; g.ldw = ldw;
+  g.m = m; g.n = n; g.k = k;
+  g.num_batches = 1;
+  g.conv_taps = 1;
+  g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16 ? 1 : 0;
+  g.q_scale = 1.f;
+  return g;
+}
+
+static int check_common(const f5_dit_weights* w, const f5_dit_buffers* b) {
+  F5_REQUIRE(w && b, "dit: null weights/buffers");
+  F5_REQUIRE(w->dim % 128 == 0 && w->dim >= 256 && w->dim <= 2048, "dit: dim %d unsupported", w->dim);
+  F5_REQUIRE(w->dim == w->heads * 64, "dit: dim %d != heads %d * 64", w->dim, w->heads);
+  F5_REQUIRE(w->mel_dim % 4 == 0 && w->mel_dim <= 128, "dit: mel_dim %d", w->mel_dim);
+  F5_REQUIRE(w->blocks && w->depth > 0, "dit: no blocks");
+  F5_REQUIRE(b->batch > 0 && b->frames > 0 && b->n_times > 0, "dit: bad buffer shape");
+  return 0;
+}
+
+}  // namespace f5
+
+using namespace f5;
+
+extern "C" int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* b, void* stream_) {
+  if (int e = device_check()) return e;
+  if (int e = check_common(w, b)) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int D = w->dim, N = b->frames, B = b->batch;
+  const int BU = (b->cfg ? 2 : 1) * B;  // row-utterances
+  const int R = BU * N;
+  const int C = w->text_dim, Ci = w->text_inner;
+
+  // ---- TextEmbedding (dit.py:196-229) for the cond rows and, with CFG, the text-dropped rows ----
+  if (int e = launch_text_embed_gather(b->text, B, b->text_len_max, N, C, w->text_emb, w->text_pos,
+                                       w->text_max_pos, b->text_x, BU,
+                                       b->cfg ? B : ((b->drop_flags & 2) ? 0 : BU), st))
+    return e;
+  for (int l = 0; l < w->conv_layers; ++l) {
+    const f5_convnext_weights& cw = w->text_blocks[l];
+    if (int e = launch_dwconv7_ln(b->text_x, b->text_a, BU, N, C, cw.dw_w, cw.dw_b, cw.ln_w, cw.ln_b, st))
+      return e;
+    {  // pwconv1 + exact GELU (convnext_v2.py:50-51)
+      f5_gemm_args g = gemm_base(b->text_a, C, cw.pw1_w, C, R, Ci, C, b->text_h, Ci, true);
+      g.bias = cw.pw1_b; g.act = F5_ACT_GELU_ERF;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+    if (int e = launch_grn(b->text_h, b->text_g, b->grn_nx, cw.grn_gamma, cw.grn_beta, BU, N, Ci, st))
+      return e;
+    {  // pwconv2 + residual, then the re-mask of dit.py:225 (masked rows have a zero residual)
+      f5_gemm_args g = gemm_base(b->text_g, Ci, cw.pw2_w, Ci, R, C, Ci, b->text_x, C, false);
+      g.bias = cw.pw2_b; g.resid = b->text_x; g.ldr = C;
+      g.rows_per_batch = N; g.num_batches = BU; g.row_len = b->text_len;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+  }
+
+  // ---- hoisted part of InputEmbedding.proj (dit.py:248-249): [cond | text] · W[:,100:]^T + b ----
+  if (int e = launch_concat_cond_text(b->cond, w->mel_dim, B, N, b->text_x, C, b->ct_bf16, w->ct_ld,
+                                      R, b->cfg ? B * N : ((b->drop_flags & 1) ? 0 : R), st))
+    return e;
+  {
+    f5_gemm_args g = gemm_base(b->ct_bf16, w->ct_ld, w->in_ct_w, w->ct_ld, R, D, w->ct_ld, b->hoist, D, false);
+    g.bias = w->in_b;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+
+  // ---- TimestepEmbedding for every evaluation time, then ALL AdaLN linears as one GEMM ----
+  if (int e = launch_time_mlp(b->tvals, b->n_times, D, w->time_w0, w->time_b0, w->time_w2,
+                              w->time_b2, nullptr, b->silu_t, st))
+    return e;
+  {
+    const int NM = w->depth * 6 * D + 2 * D;
+    f5_gemm_args g = gemm_base(b->silu_t, D, w->mod_w, D, b->n_times, NM, D, b->mod_table, NM, false);
+    g.bias = w->mod_b;
+    g.tile_n = 128;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+  return 0;
+}
+
+extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, int32_t ti,
+                              void* stream_) {
+  if (int e = device_check()) return e;
+  if (int e = check_common(w, b)) return e;
+  F5_REQUIRE(ti >= 0 && ti < b->n_times, "dit_forward: time_index %d out of [0,%d)", ti, b->n_times);
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int D = w->dim, N = b->frames, F = w->ff_inner;
+  const int BU = (b->cfg ? 2 : 1) * b->batch;
+  const int R = BU * N;
+  const int NM = w->depth * 6 * D + 2 * D;
+  const float* mod = b->mod_table + (size_t)ti * NM;
+
+  // ---- InputEmbedding (dit.py:249-251): x·Wx + hoist, then + ConvPositionEmbedding ----
+  {
+    f5_gemm_args g = gemm_base(b->y_bf16, 128, w->in_x_w, 128, R, D, 128, b->h, D, false);
+    g.resid = b->hoist; g.ldr = D;
+    g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+  {
+    f5_gemm_args g = gemm_base(b->a_bf16, D, w->conv_w[0], 31 * 64, R, D, 64, b->c_bf16, D, true);
+    g.bias = w->conv_b[0]; g.act = F5_ACT_MISH;
+    g.rows_per_batch = N; g.num_batches = BU; g.batched_tiles = 1;
+    g.conv_taps = 31; g.conv_pad = 15; g.conv_grouped = 1;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+  {
+    f5_gemm_args g = gemm_base(b->c_bf16, D, w->conv_w[1], 31 * 64, R, D, 64, b->x, D, false);
+    g.bias = w->conv_b[1]; g.act = F5_ACT_MISH;
+    g.rows_per_batch = N; g.num_batches = BU; g.batched_tiles = 1;
+    g.conv_taps = 31; g.conv_pad = 15; g.conv_grouped = 1;
+    g.resid = b->h; g.ldr = D;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+
+  // ---- transformer blocks (dit.py:311-325) ----
+  for (int l = 0; l < w->depth; ++l) {
+    const f5_dit_block_weights& bw = w->blocks[l];
+    const float* m = mod + (size_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + D, m, 0, 1, st)) return e;
+    {
+      f5_gemm_args g = gemm_base(b->a_bf16, D, bw.qkv_w, D, R, 3 * D, D, b->qkv_bf16, 3 * D, true);
+      g.bias = bw.qkv_b;
+      g.rows_per_batch = N; g.num_batches = BU;
+      g.rope = b->rope; g.rope_cols = 2 * D; g.q_scale = 0.125f; g.q_cols = D;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+    if (int e = f5_attention_fwd(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64, b->seq_len, st))
+      return e;
+    {
+      f5_gemm_args g = gemm_base(b->c_bf16, D, bw.out_w, D, R, D, D, b->x, D, false);
+      g.bias = bw.out_b;
+      g.rows_per_batch = N; g.num_batches = BU; g.row_len = b->seq_len;
+      g.gate = m + 2 * D; g.gate_ld = 0;
+      g.resid = b->x; g.ldr = D;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + 4 * D, m + 3 * D, 0, 1, st)) return e;
+    {
+      f5_gemm_args g = gemm_base(b->a_bf16, D, bw.ff1_w, D, R, F, D, b->ff_bf16, F, true);
+      g.bias = bw.ff1_b; g.act = F5_ACT_GELU_TANH;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+    {
+      f5_gemm_args g = gemm_base(b->ff_bf16, F, bw.ff2_w, F, R, D, F, b->x, D, false);
+      g.bias = bw.ff2_b;
+      g.rows_per_batch = N; g.num_batches = BU;
+      g.gate = m + 5 * D; g.gate_ld = 0;
+      g.resid = b->x; g.ldr = D;
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
+  }
+
+  // ---- AdaLayerNormZero_Final (scale first, dit.py:287) + proj_out (dit.py:398-399) ----
+  {
+    const float* mf = mod + (size_t)w->depth * 6 * D;
+    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, mf, mf + D, 0, 1, st)) return e;
+    f5_gemm_args g = gemm_base(b->a_bf16, D, w->proj_w, D, R, w->mel_dim, D, b->v, w->mel_dim, false);
+    g.bias = w->proj_b;
+    if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+  return 0;
+}
+
+// Evaluation times in the order the solvers call fn (cfm.py:50-59, 76-89, 106-120), computed in
+// fp32 exactly as the reference does (t_current + 0.5 * dt etc.).
+extern "C" int f5_ode_eval_times(const float* t, int32_t steps, int32_t method, float* out,
+                                 int32_t cap) {
+  F5_REQUIRE(t && steps >= 2, "ode_eval_times: need >= 2 grid points");
+  F5_REQUIRE(method >= 0 && method <= 2, "ode_eval_times: unknown method %d", method);
+  const int per = method == 0 ? 1 : (method == 1 ? 2 : 4);
+  const int n = (steps - 1) * per;
+  if (out == nullptr) return n;
+  F5_REQUIRE(cap >= n, "ode_eval_times: capacity %d < %d", cap, n);
+  int k = 0;
+  for (int i = 0; i + 1 < steps; ++i) {
+    const float tc = t[i];
+    const float dt = t[i + 1] - tc;
+    out[k++] = tc;
+    if (method == 1) {
+      out[k++] = tc + 0.5f * dt;
+    } else if (method == 2) {
+      out[k++] = tc + 0.5f * dt;
+      out[k++] = tc + 0.5f * dt;
+      out[k++] = tc + dt;
+    }
+  }
+  return n;
+}
+
+extern "C" int f5_ode_sample(const f5_dit_weights* w, const f5_dit_buffers* b, const float* t,
+                             int32_t steps, int32_t method, float cfg_strength, float* y,
+                             float* trajectory, float* scratch, void* stream_) {
+  if (int e = device_check()) return e;
+  if (int e = check_common(w, b)) return e;
+  F5_REQUIRE(t && steps >= 2 && y, "ode_sample: bad arguments");
+  F5_REQUIRE(method >= 0 && method <= 2, "ode_sample: unknown method %d", method);
+  F5_REQUIRE((cfg_strength >= 1e-5f) == (b->cfg != 0),
+             "ode_sample: buffers built with cfg=%d but cfg_strength=%g", b->cfg, cfg_strength);
+  const int per = method == 0 ? 1 : (method == 1 ? 2 : 4);
+  F5_REQUIRE(b->n_times == (steps - 1) * per, "ode_sample: n_times %d != %d", b->n_times,
+             (steps - 1) * per);
+  F5_REQUIRE(method == 0 || scratch, "ode_sample: scratch required for midpoint/rk4");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int BN = b->batch * b->frames, d = w->mel_dim;
+  const size_t state = (size_t)BN * d;
+  const long long dup = b->cfg ? BN : 0;
+
+  // A operand of the first x-projection: bf16(y0), both CFG halves
+  const float* y_cur = trajectory ? trajectory : y;
+  if (int e = launch_cast_pad_bf16(y_cur, d, b->y_bf16, 128, BN, dup, st)) return e;
+
+  OdeUpdateParams u;
+  memset(&u, 0, sizeof(u));
+  u.v = b->v; u.ldv = d; u.null_row_offset = dup; u.cfg_strength = cfg_strength;
+  u.y_bf16 = reinterpret_cast<__nv_bfloat16*>(b->y_bf16); u.ld_bf16 = 128;
+  u.bf16_copy_row_offset = dup;
+  u.rows = BN; u.d = d;
+  float* y_tmp = scratch;
+  float* k_acc = scratch ? scratch + state : nullptr;
+
+  int ti = 0;
+  for (int i = 0; i + 1 < steps; ++i) {
+    const float dt = t[i + 1] - t[i];
+    float* y_next = trajectory ? trajectory + (size_t)(i + 1) * state : y;
+    u.y_base = y_cur;
+    if (method == 0) {
+      if (int e = f5_dit_forward(w, b, ti++, st)) return e;
+      u.y_out = y_next; u.a = dt; u.k_acc = nullptr; u.use_acc = 0;
+      if (int e = launch_ode_update(u, st)) return e;
+    } else if (method == 1) {
+      if (int e = f5_dit_forward(w, b, ti++, st)) return e;
+      u.y_out = y_tmp; u.a = 0.5f * dt; u.k_acc = nullptr; u.use_acc = 0;
+      if (int e = launch_ode_update(u, st)) return e;
+      if (int e = f5_dit_forward(w, b, ti++, st)) return e;
+      u.y_out = y_next; u.a = dt;
+      if (int e = launch_ode_update(u, st)) return e;
+    } else {
+      const float as[4] = {0.5f * dt, 0.5f * dt, dt, dt / 6.f};
+      const float ws[4] = {1.f, 2.f, 2.f, 1.f};
+      for (int s = 0; s < 4; ++s) {
+        if (int e = f5_dit_forward(w, b, ti++, st)) return e;
+        u.k_acc = k_acc; u.acc_w = ws[s]; u.acc_init = (s == 0); u.use_acc = (s == 3);
+        u.y_out = (s == 3) ? y_next : y_tmp; u.a = as[s];
+        if (int e = launch_ode_update(u, st)) return e;
+      }
+    }
+    y_cur = y_next;
+  }
+  return 0;
+}

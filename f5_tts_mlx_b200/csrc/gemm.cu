@@ -93,6 +93,9 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
   p.rope_cols = a->rope_cols;
   p.q_scale = a->q_scale;
   p.q_cols = a->q_cols;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16);
+  p.ldo2 = (int)a->ldo2;
+  if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows
   CUtensorMap ta, tb;

@@ -53,6 +53,8 @@ struct GemmParams {
   int rope_cols;
   float q_scale;
   int q_cols;
+  __nv_bfloat16* out2;     // optional bf16 copy of the result
+  int ldo2;
 };
 
 template <int BN, int kStages>
@@ -247,6 +249,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
             if (col0 + j < p.N) {
               float4 x = *reinterpret_cast<const float4*>(rr + j);
               v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+            }
+          }
+        }
+        if (p.out2 != nullptr) {
+          __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j < p.N) {
+              uint4 w;
+              w.x = pack_bf16x2(v[j], v[j + 1]);
+              w.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              w.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              w.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o2 + j) = w;
             }
           }
         }

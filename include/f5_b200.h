@@ -80,9 +80,202 @@ typedef struct f5_gemm_args {
   float q_scale;          /* columns [0, q_cols) are multiplied by q_scale after the rotation   */
   int32_t q_cols;
   int32_t tile_n;         /* 0 = auto, else 64 | 128                                            */
+  void* out2_bf16;        /* optional second copy of the result as bf16 [rows, ldo2], or NULL    */
+  int64_t ldo2;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Flash-attention forward (non-causal, key-padding mask, head_dim 64) — replaces
+ * mx.fast.scaled_dot_product_attention + head split/merge at dit.py:141-143,161-167.
+ * qkv: bf16 [batch*frames, ld_qkv] = [q | k | v], each heads*64 wide, q pre-scaled by 1/sqrt(64)
+ * and q,k already rotated (f5_gemm_bf16 epilogue).  out: bf16 [batch*frames, ld_out].
+ * kv_len: int32 [batch] valid keys per utterance or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch,
+                     int32_t frames, int32_t heads, int32_t head_dim, const int32_t* kv_len,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * HBM-bound pieces.
+ * f5_ln_modulate : nn.LayerNorm(affine=False, eps=1e-6)(x) * (add_one + scale[b]) + shift[b]
+ *                  (AdaLayerNormZero dit.py:270,289,321; with add_one=0 and mod_batch_stride=0 it
+ *                  is the affine nn.LayerNorm of convnext_v2.py:38).  x fp32 -> y bf16.
+ * f5_dwconv7_ln  : depthwise Conv1d(k=7,pad=3)+bias then affine LayerNorm (convnext_v2.py:35-38,
+ *                  48-49).  x fp32 [batch, frames, C]; w_tap_major fp32 [7, C]; y bf16.
+ * f5_grn         : GRN over the frame axis (convnext_v2.py:15-18). h,y bf16 [batch, frames, C];
+ *                  nx_scratch fp32 [batch, C].
+ * ------------------------------------------------------------------------------------------ */
+int f5_ln_modulate(const float* x, void* y_bf16, int32_t rows, int32_t dim, int32_t rows_per_batch,
+                   const float* scale, const float* shift, int64_t mod_batch_stride,
+                   int32_t add_one, void* stream);
+int f5_dwconv7_ln(const float* x, void* y_bf16, int32_t batch, int32_t frames, int32_t channels,
+                  const float* w_tap_major, const float* bias, const float* ln_w, const float* ln_b,
+                  void* stream);
+int f5_grn(const void* h_bf16, void* y_bf16, float* nx_scratch, const float* gamma,
+           const float* beta, int32_t batch, int32_t frames, int32_t channels, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * DiT (dit.py:331-401) and the ODE loop of F5TTS.sample (cfm.py:340-393).
+ *
+ * Weight layout ("packed"): what f5_tts_mlx_b200.weights.pack_dit() produces from the MLX
+ * parameter tree: Linear weights bf16 (out,in); q/k/v fused row-wise into one
+ * [3D, D] matrix; the per-block AdaLN linears (dit.py:263,282) concatenated row-wise into one
+ * [depth*6D + 2D, D] matrix so the modulation vectors of ALL ODE time points are one GEMM; the
+ * grouped k=31 convs (dit.py:33-38) as [D, 31*64] tap-major block-diagonal-by-64; the input
+ * projection (dit.py:239) split by source: columns of x (padded to 128) and of [cond|text]
+ * (padded to a multiple of 64).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct f5_convnext_weights {
+  const float* dw_w;   /* fp32 [7, C] tap-major (MLX (C,7,1) transposed) */
+  const float* dw_b;   /* [C] */
+  const float* ln_w;   /* [C] */
+  const float* ln_b;
+  const void* pw1_w;   /* bf16 [Ci, C] */
+  const float* pw1_b;
+  const float* grn_gamma; /* [Ci] */
+  const float* grn_beta;
+  const void* pw2_w;   /* bf16 [C, Ci] */
+  const float* pw2_b;
+} f5_convnext_weights;
+
+typedef struct f5_dit_block_weights {
+  const void* qkv_w;  const float* qkv_b;   /* bf16 [3D, D], fp32 [3D]   (dit.py:119-121) */
+  const void* out_w;  const float* out_b;   /* [D, D]                     (dit.py:124)     */
+  const void* ff1_w;  const float* ff1_b;   /* [F, D]                     (dit.py:94-95)   */
+  const void* ff2_w;  const float* ff2_b;   /* [D, F]                     (dit.py:96)      */
+} f5_dit_block_weights;
+
+typedef struct f5_dit_weights {
+  int32_t dim, depth, heads, ff_inner, mel_dim, text_dim, text_inner, conv_layers;
+  int32_t text_rows;     /* rows of the embedding table (text_num_embeds + 1) */
+  int32_t text_max_pos;  /* 4096 (dit.py:190) */
+  int32_t ct_ld;         /* padded width of [cond|text] (multiple of 64) */
+  int32_t reserved;
+  const float* time_w0; const float* time_b0;   /* fp32 [D,256],[D]   (dit.py:77) */
+  const float* time_w2; const float* time_b2;   /* fp32 [D,D],[D] */
+  const float* text_emb;                        /* fp32 [text_rows, text_dim] */
+  const float* text_pos;                        /* fp32 [text_max_pos, text_dim] (rope.py:63-73) */
+  const f5_convnext_weights* text_blocks;       /* HOST array [conv_layers] */
+  const void* in_x_w;                           /* bf16 [D, 128] */
+  const void* in_ct_w;                          /* bf16 [D, ct_ld] */
+  const float* in_b;                            /* fp32 [D] */
+  const void* conv_w[2]; const float* conv_b[2];/* bf16 [D, 31*64], fp32 [D] */
+  const void* mod_w; const float* mod_b;        /* bf16 [depth*6D+2D, D], fp32 */
+  const f5_dit_block_weights* blocks;           /* HOST array [depth] */
+  const void* proj_w; const float* proj_b;      /* bf16 [mel_dim, D], fp32 [mel_dim] */
+} f5_dit_weights;
+
+/* Caller-allocated device buffers for one sampling session of `batch` utterances padded to
+ * `frames`.  rows = (cfg ? 2 : 1) * batch * frames: with classifier-free guidance the
+ * conditional and unconditional passes of cfm.py:342-363 run as ONE forward over a doubled batch
+ * (cond rows first). */
+typedef struct f5_dit_buffers {
+  int32_t batch, frames, cfg, n_times;
+  int32_t text_len_max;       /* nt: columns of `text` */
+  int32_t drop_flags;         /* only when cfg == 0: bit0 drop_audio_cond, bit1 drop_text (dit.py:380-381) */
+  /* inputs */
+  const int32_t* text;        /* int32 [batch, nt], pad -1 */
+  const int32_t* text_len;    /* int32 [rows/frames]: valid tokens (<= frames) per row-utterance */
+  const int32_t* seq_len;     /* int32 [rows/frames] valid frames, or NULL when mask is None */
+  const float* cond;          /* fp32 [batch, frames, mel_dim] step_cond (cfm.py:331) */
+  const float* tvals;         /* fp32 [n_times] DiT evaluation times, in evaluation order */
+  const float* rope;          /* fp32 [frames, 32, 2] cos/sin of n*theta_i (rope.py:38-53) */
+  /* precomputed by f5_dit_precompute */
+  float* hoist;               /* fp32 [rows, D]: cond·Wc + text·Wt + b (dit.py:249, step-invariant) */
+  float* mod_table;           /* fp32 [n_times, depth*6D+2D] */
+  /* scratch */
+  float* text_x;              /* fp32 [rows, text_dim] */
+  void* text_a;               /* bf16 [rows, text_dim] */
+  void* text_h;               /* bf16 [rows, text_inner] */
+  void* text_g;               /* bf16 [rows, text_inner] */
+  float* grn_nx;              /* fp32 [rows/frames, text_inner] */
+  void* ct_bf16;              /* bf16 [rows, ct_ld] */
+  void* silu_t;               /* bf16 [n_times, D] */
+  void* y_bf16;               /* bf16 [rows, 128]: current ODE state, A operand of the x-projection */
+  float* x;                   /* fp32 [rows, D] residual stream */
+  float* h;                   /* fp32 [rows, D] */
+  void* a_bf16;               /* bf16 [rows, D] */
+  void* c_bf16;               /* bf16 [rows, D] */
+  void* qkv_bf16;             /* bf16 [rows, 3D] */
+  void* ff_bf16;              /* bf16 [rows, ff_inner] */
+  float* v;                   /* fp32 [rows, mel_dim]: DiT output (flow prediction) */
+} f5_dit_buffers;
+
+/* step-invariant work, once per sample(): text embedding (dit.py:196-229), hoisted conditioning
+ * projection, TimestepEmbedding + every AdaLN linear for all n_times (dit.py:73-82,267,286). */
+int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* b, void* stream);
+/* one DiT evaluation (dit.py:374-401) at tvals[time_index] on the state in b->y_bf16 -> b->v */
+int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, int32_t time_index, void* stream);
+
+/* Fixed-grid explicit ODE solve (cfm.py:38-122, 340-393).  t_grid: HOST fp32 [steps] (the sway-
+ * warped grid, `steps` grid points = steps-1 intervals).  method: 0 euler, 1 midpoint, 2 rk4.
+ * b->tvals / n_times must hold the evaluation times in the order the solver visits them (see
+ * f5_ode_eval_times).  y: fp32 [batch*frames, mel_dim] initial noise, overwritten by the final
+ * state unless `trajectory` (fp32 [steps, batch*frames, mel_dim]) is given, in which case
+ * trajectory[0] must hold y0 and every state is stored (cfm.py:61).  scratch: fp32
+ * [2, batch*frames, mel_dim]. */
+int f5_ode_eval_times(const float* h_t_grid, int32_t steps, int32_t method, float* h_out, int32_t cap);
+int f5_ode_sample(const f5_dit_weights* w, const f5_dit_buffers* b, const float* h_t_grid,
+                  int32_t steps, int32_t method, float cfg_strength, float* y, float* trajectory,
+                  float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Log-mel front-end — replaces log_mel_spectrogram / MelSpec (audio.py:162-230): zero-padded
+ * centred frames (n_fft 1024), periodic Hann, real FFT, magnitude, HTK filterbank, log(max(.,1e-5)),
+ * LAST FRAME DROPPED (audio.py:203) => frames = samples / hop.
+ * audio fp32 [batch, samples]; window fp32 [1024]; filters_t fp32 [513, n_mels] (filterbank
+ * transposed); out fp32 [batch, frames, n_mels].
+ * ------------------------------------------------------------------------------------------ */
+int f5_mel_forward(const float* audio, int32_t batch, int32_t samples, const float* window,
+                   const float* filters_t, int32_t n_mels, int32_t hop, float* out, int32_t frames,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Vocos vocoder — replaces vocos_mlx.Vocos.decode (third-party; call sites cfm.py:399-400,446,
+ * 471): Conv1d(100->512,k7) LN 8x[dwconv7 LN Linear GELU Linear gamma* +res] LN Linear(512->1026)
+ * -> (log-mag, phase) -> ISTFT(n_fft 1024, hop 256).
+ * f5_istft: h fp32 [batch*frames, ldh] = [log-mag 513 | phase 513 | pad]; per-frame inverse real
+ * FFT, windowed overlap-add, divided by the window envelope (norm_sq 0: sum w — vocos-mlx;
+ * 1: sum w^2 — torch.istft), `trim` leading samples dropped.  out fp32 [batch, out_len].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct f5_vocos_block_weights {
+  const float* dw_w; const float* dw_b;      /* fp32 [7, D] tap-major, [D] */
+  const float* ln_w; const float* ln_b;
+  const void* pw1_w; const float* pw1_b;     /* bf16 [Ci, D] */
+  const void* pw2_w; const float* pw2_b;     /* bf16 [D, Ci] */
+  const float* gamma;                        /* fp32 [D] layer scale */
+} f5_vocos_block_weights;
+
+typedef struct f5_vocos_weights {
+  int32_t n_mels, dim, inner, num_layers;
+  int32_t head_ld;        /* padded width of the head output (1028) */
+  int32_t hop, istft_norm_sq, istft_trim;
+  const void* embed_w; const float* embed_b;     /* bf16 [D, 7*128] tap-major, fp32 [D] */
+  const float* norm_w; const float* norm_b;
+  const f5_vocos_block_weights* blocks;          /* HOST array [num_layers] */
+  const float* final_w; const float* final_b;
+  const void* head_w; const float* head_b;       /* bf16 [head_ld, D], fp32 [head_ld] */
+  const float* window;                           /* fp32 [1024] periodic Hann */
+} f5_vocos_weights;
+
+typedef struct f5_vocos_buffers {
+  int32_t batch, frames, out_len, reserved;
+  void* mel_bf16;      /* bf16 [R, 128]   R = batch*frames */
+  float* h;            /* fp32 [R, D] */
+  float* x;            /* fp32 [R, D] */
+  void* a_bf16;        /* bf16 [R, D] */
+  void* i_bf16;        /* bf16 [R, inner] */
+  float* head;         /* fp32 [R, head_ld] */
+  float* frames_f32;   /* fp32 [R, 1024] */
+} f5_vocos_buffers;
+
+int f5_istft(const float* h, int64_t ldh, int32_t batch, int32_t frames, const float* window,
+             int32_t hop, int32_t norm_sq, int32_t trim, float* frames_scratch, float* out,
+             int32_t out_len, void* stream);
+int f5_vocos_decode(const f5_vocos_weights* w, const f5_vocos_buffers* b, const float* mel,
+                    float* wave, void* stream);
 
 #ifdef __cplusplus
 }
