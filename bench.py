@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — mel-frames/sec of the F5TTS.sample() hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one F5TTS.sample() ODE solve of one batch of synthetic utterances per GPU
+(default workload = BASELINE.json configs[1]: F5-TTS base 22-layer/1024-dim/16-head DiT, 10 s
+utterance = 937 mel frames (328 ref + 609 gen), 152 text tokens, Euler, steps=32 grid points
+(31 intervals, 62 DiT evaluations with CFG=2), batch 1 per GPU).  Weights are seeded random
+(no checkpoints are reachable), inputs synthetic.
+
+  value      : whole-job mel-frames/s, inputs resident in HBM (CUDA-graph replay of the loop)
+  e2e        : same metric through the public API a user calls — F5TTS.sample(raw wave on the
+               HOST, text) -> waveform on the HOST: H2D of the reference audio + noise, log-mel
+               front-end, ODE loop, Vocos vocoder, D2H of the waveform, all inside the timed region
+  roofline   : tcgen05 GEMM family (the dominant kernels): algorithmic FLOPs / summed device time
+               of its launches in one eager step bracketed by CUDA events on the launch stream
+  cpu_baseline: the CPU oracle (torch-CPU fp32 restatement of the reference — MLX itself is not
+               installable here) timed on this box's host cores on a bounded sample of the SAME
+               workload
+  --impl reference : times only that CPU restatement (rank 0), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, HOP = 24000, 256
+TOTAL_SAMPLES, REF_SAMPLES, N_TEXT = 240000, 84000, 152      # SURVEY §8d synthetic "10 s" utterance
+
+
+def synth_audio(length: int, seed: int) -> torch.Tensor:
+    rng = np.random.default_rng(seed)
+    t = np.arange(length) / SR
+    f0 = 110 + 110 * rng.random()
+    x = sum(np.sin(2 * np.pi * f0 * (h + 1) * t + rng.random() * 6.28) / (h + 1) for h in range(8))
+    x = x * (0.6 + 0.4 * np.sin(2 * np.pi * 1.3 * t)) + 0.01 * rng.standard_normal(length)
+    return torch.from_numpy((x * 0.1 / np.sqrt(np.mean(x ** 2))).astype(np.float32))
+
+
+def synth_inputs(batch: int, frames: int, ref_frames: int, seed: int):
+    g = torch.Generator().manual_seed(seed)
+    cond = (torch.randn(batch, ref_frames, 100, generator=g) * 2.24 - 1.27).clamp(-11.51, 5.0)
+    text = torch.randint(0, 2545, (batch, N_TEXT), generator=g, dtype=torch.int32)
+    y0 = torch.randn(batch, 100, frames, generator=g).permute(0, 2, 1).contiguous()
+    return cond, text, y0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md (sustained 1.4 PF)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline / --impl reference)
+# ---------------------------------------------------------------------------------------------
+def oracle_step(args, W, ocfg, intervals: int, seed: int):
+    """Bounded sample of the workload: `intervals` solver intervals of ONE utterance of the same
+    shape, run exactly like the reference (two unbatched CFG passes, text embedding per forward).
+    Returns (seconds, frames/s extrapolated to the full grid)."""
+    from oracle import f5_oracle as O
+    frames, ref_frames = args.frames, args.ref_frames
+    cond, text, y0 = synth_inputs(1, frames, ref_frames, seed)
+    full_t = O.time_grid(args.ode_steps, -1.0)
+    prep = O.sample_prologue(cond, text, frames, W)
+    solver = {"euler": O.odeint_euler, "midpoint": O.odeint_midpoint, "rk4": O.odeint_rk4}[args.method]
+
+    def fn(t, x):
+        pred = O.dit_forward(x, prep.step_cond, prep.text, t, False, False, prep.mask, W, ocfg)
+        null = O.dit_forward(x, prep.step_cond, prep.text, t, True, True, prep.mask, W, ocfg)
+        return pred + (pred - null) * args.cfg
+
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        solver(fn, y0, full_t[: intervals + 1])
+    dt = time.perf_counter() - t0
+    full = dt * (args.ode_steps - 1) / intervals
+    return dt, frames / full
+
+
+def oracle_setup(args):
+    from oracle import f5_oracle as O
+    from f5_tts_mlx_b200.weights import BASE_CONFIG, random_dit_weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = BASE_CONFIG
+    W = random_dit_weights(cfg, seed=1234)
+    ocfg = O.DiTConfig(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult,
+                       text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers)
+    return W, ocfg
+
+
+def workload_config(args, world: int) -> dict:
+    return {"workload": f"F5-TTS base DiT 22L/1024d/16h, {args.batch} x 10 s utterance per GPU "
+                        f"({args.frames} mel frames = {args.ref_frames} ref + {args.frames - args.ref_frames} gen, "
+                        f"{N_TEXT} text tokens), {args.method} steps={args.ode_steps} grid points "
+                        f"({args.ode_steps - 1} intervals), CFG={args.cfg}, sway=-1",
+            "global_batch": args.batch * world, "frames": args.frames, "parallelism": f"dp{world}",
+            "l2": "no flush: the 0.67 GB of bf16 weights streamed every DiT evaluation exceed the 126 MB L2"}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    W, ocfg = oracle_setup(args)
+    intervals = 2
+    for _ in range(args.warmup):
+        oracle_step(args, W, ocfg, 1, 0)
+    times, fps = [], []
+    for i in range(args.steps):
+        dt, f = oracle_step(args, W, ocfg, intervals, i)
+        times.append(dt); fps.append(f)
+    val = args.frames * len(fps) / sum(args.frames / f for f in fps)
+    cores = torch.get_num_threads()
+    sample = (f"{intervals} of {args.ode_steps - 1} {args.method} intervals ({2 * intervals} DiT evaluations with CFG) of one "
+              f"{args.frames}-frame utterance per step, extrapolated x{(args.ode_steps - 1) / intervals:.1f}")
+    line = {"impl": "reference", "metric": "mel-frames/sec", "value": val, "unit": "mel-frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "torch-CPU fp32 restatement of the reference (oracle/f5_oracle.py); MLX is not "
+                                     "installable in this image"},
+            "e2e": {"value": val, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    import ctypes as C
+    from f5_tts_mlx_b200 import BASE_CONFIG, DiT, F5TTS, _lib
+    from f5_tts_mlx_b200.vocos import Vocos
+    from f5_tts_mlx_b200.weights import VocosConfig, random_dit_weights, random_vocos_weights
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    cfg = BASE_CONFIG
+    model = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
+                text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev)
+    # rank 0 builds + packs the weights; ONE broadcast of the packed buffer (the only collective)
+    if rank == 0:
+        model.load_weights(random_dit_weights(cfg, seed=1234))
+    else:
+        model.allocate_weights()
+    if world > 1:
+        model.packed.broadcast(src=0)
+    vocos = Vocos(VocosConfig(), dev).load_weights(random_vocos_weights())
+    f5 = F5TTS(model)
+    f5_e2e = F5TTS(model, vocoder=vocos.decode)
+
+    B, N, NR = args.batch, args.frames, args.ref_frames
+    cond, text, y0 = synth_inputs(B, N, NR, seed=100 + rank)
+    cond_d, y0_d = cond.to(dev), y0.to(dev)
+    kw = dict(steps=args.ode_steps, method=args.method, cfg_strength=args.cfg, sway_sampling_coef=-1.0,
+              return_trajectory=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also captures the CUDA graph) ----
+    for _ in range(max(args.warmup, 3)):
+        out, _ = f5.sample(cond_d, text, N, y0=y0_d, **kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all().item(), "non-finite output"
+    plan = f5.last_plan
+
+    # ---- launches per step + per-family device time: one eager step under event brackets ----
+    f5.use_cuda_graph = False
+    c0 = lib.f5_launch_count()
+    lib.f5_prof_enable(1)
+    f5.sample(cond_d, text, N, y0=y0_d, **kw)
+    torch.cuda.synchronize()
+    prof = (C.c_double * 16)()
+    lib.f5_prof_summary(prof, 4)
+    lib.f5_prof_enable(0)
+    launches_per_step = int(lib.f5_launch_count() - c0)
+    f5.use_cuda_graph = True
+    fam = {k: {"ms": prof[i * 4], "flops": prof[i * 4 + 1], "bytes": prof[i * 4 + 2], "launches": int(prof[i * 4 + 3])}
+           for i, k in enumerate(("gemm", "attention", "ln_modulate", "other"))}
+
+    # ---- timed region: K steps, inputs resident in HBM, graph replay ----
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.y.copy_(y0_d)
+        plan.run(f5, True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = world * B * N * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with HOST buffers ----
+    audio_h = synth_audio(REF_SAMPLES, seed=7 + rank).pin_memory()
+    y0_h = y0[:1].contiguous().pin_memory()
+    text1 = text[:1]
+    e2e_steps = max(2, min(args.steps, 10))
+
+    def e2e_once():
+        a = audio_h.to(dev, non_blocking=True)[None]
+        wave, _ = f5_e2e.sample(a, text1, N, y0=y0_h.to(dev, non_blocking=True), **kw)
+        return wave.to("cpu", non_blocking=False)
+
+    for _ in range(3):
+        w = e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        w = e2e_once()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * 1 * N * e2e_steps / te.item()
+    h2d = audio_h.numel() * 4 + y0_h.numel() * 4 + text1.numel() * 4
+    d2h = w.numel() * 4
+
+    if rank != 0:
+        return
+    pk = peaks()
+    g = fam["gemm"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    a = fam["attention"]
+    total_ms = sum(v["ms"] for v in fam.values())
+    from oracle import f5_oracle as O
+    ocfg = O.DiTConfig()
+    n_fwd = O.dit_forwards_per_sample(args.ode_steps, args.method, args.cfg)
+    alg_flops_step = n_fwd * O.dit_forward_flops(N, ocfg) * B
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"], "traffic": None,
+            "kernel": "gemm_bf16_tn_kernel (tcgen05, all shapes of one step)",
+            "of": pk["source"],
+            "gemm_share_of_step_device_time": g["ms"] / total_ms if total_ms else None,
+            "attention": {"achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0,
+                          "share_of_step_device_time": a["ms"] / total_ms if total_ms else None},
+            "whole_step": {"algorithmic_tflop": alg_flops_step / 1e12,
+                           "achieved_tflops": alg_flops_step * world / (ms_total / args.steps * 1e-3) / 1e12,
+                           "frac": alg_flops_step / (ms_total / args.steps * 1e-3) / 1e12 / pk["bf16_tflops"]}}
+
+    # CPU baseline beside it (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        W, ocfg2 = oracle_setup(args)
+        oracle_step(args, W, ocfg2, 1, 0)
+        dt, fps = oracle_step(args, W, ocfg2, 4, 1)
+        cpu = {"value": fps, "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"4 of {args.ode_steps - 1} {args.method} intervals of one {N}-frame utterance ({dt:.1f} s of CPU), "
+                         f"extrapolated to the full grid",
+               "note": "torch-CPU fp32 restatement of the reference (MLX unavailable in this image)"}
+    line = {"metric": "mel-frames/sec", "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "F5TTS.sample(host raw wave, text) -> mel kernel -> ODE loop -> Vocos -> host waveform",
+                    "ms_per_step": 1e3 * te.item() / e2e_steps},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu,
+            "rtf": (ms_total / args.steps / 1e3) / ((N - NR) * HOP / SR)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step")
+    ap.add_argument("--frames", type=int, default=TOTAL_SAMPLES // HOP)
+    ap.add_argument("--ref-frames", type=int, default=REF_SAMPLES // HOP)
+    ap.add_argument("--ode-steps", type=int, default=32)
+    ap.add_argument("--method", default="euler", choices=["euler", "midpoint", "rk4"])
+    ap.add_argument("--cfg", type=float, default=2.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 10:
+            args.steps = 10
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_cuda(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

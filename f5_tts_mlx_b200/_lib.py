@@ -66,6 +66,9 @@ SYMBOLS: dict[str, tuple] = {
     "f5_last_error": (C.c_char_p, []),
     "f5_abi_version": (C.c_int, []),
     "f5_device_check": (C.c_int, []),
+    "f5_launch_count": (C.c_longlong, []),
+    "f5_prof_enable": (C.c_int, [C.c_int]),
+    "f5_prof_summary": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "f5_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -78,6 +81,11 @@ SYMBOLS: dict[str, tuple] = {
     "f5_dit_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_dit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "f5_ode_eval_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32]),
+    "f5_mel_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_int32, C.c_void_p]),
+    "f5_istft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                           C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "f5_vocos_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_ode_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

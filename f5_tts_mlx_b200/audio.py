@@ -40,7 +40,8 @@ def hanning(size: int) -> torch.Tensor:
 
 @lru_cache(maxsize=8)
 def _tables(sample_rate: int, n_fft: int, n_mels: int, device: str):
-    return hanning(n_fft).to(device), mel_filters(sample_rate, n_fft, n_mels).to(device)
+    # the kernel wants the filterbank transposed: [n_fft//2+1, n_mels]
+    return hanning(n_fft).to(device), mel_filters(sample_rate, n_fft, n_mels).T.contiguous().to(device)
 
 
 def log_mel_spectrogram(audio: torch.Tensor, sample_rate: int = 24_000, n_mels: int = 100, n_fft: int = 1024,
@@ -56,7 +57,9 @@ def log_mel_spectrogram(audio: torch.Tensor, sample_rate: int = 24_000, n_mels: 
     if n_fft != 1024:
         raise NotImplementedError("f5_mel_forward implements the path's n_fft = 1024")
     b, t = audio.shape
-    frames = (t + n_fft - n_fft + hop_length) // hop_length - 1   # stft frame count minus the dropped last frame
+    # stft yields (t + 2*(n_fft//2) - n_fft + hop) // hop frames (audio.py:156) and the last one is
+    # dropped (audio.py:203): t // hop frames remain
+    frames = (t + hop_length) // hop_length - 1
     window, filters = _tables(sample_rate, n_fft, n_mels, str(audio.device))
     out = torch.empty(b, max(frames, 0), n_mels, device=audio.device, dtype=torch.float32)
     if frames > 0:

@@ -29,6 +29,8 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
     attr_set = true;
   }
   dim3 grid(cdiv(frames, 128), heads, batch);
+  ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
+               2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
   attn_fwd_kernel<<<grid, 192, AttnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream_)>>>(tm, p);
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;

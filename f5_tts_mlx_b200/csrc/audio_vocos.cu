@@ -148,6 +148,8 @@ int f5_mel_forward(const float* audio, int32_t batch, int32_t samples, const flo
   F5_REQUIRE(batch > 0 && samples > 0 && frames > 0 && n_mels > 0, "f5_mel_forward: bad shape");
   F5_REQUIRE(frames <= samples / hop, "f5_mel_forward: frames %d > samples/hop %d", frames,
              samples / hop);
+  ProfScope ps(PROF_OTHER, 0.0, 4.0 * batch * (double)samples + 4.0 * batch * (double)frames * n_mels,
+               (cudaStream_t)stream);
   mel_kernel<<<dim3(cdiv(frames, kMelWarps), batch), kMelWarps * 32, 0, (cudaStream_t)stream>>>(
       audio, samples, window, filters, n_mels, hop, out, frames);
   F5_CHECK_CUDA(cudaGetLastError());
@@ -162,6 +164,7 @@ int f5_istft(const float* h, int64_t ldh, int32_t batch, int32_t frames, const f
   F5_REQUIRE(ldh >= 1026, "f5_istft: ldh %lld < 1026", (long long)ldh);
   const int rows = batch * frames;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   istft_frames_kernel<<<cdiv(rows, kMelWarps), kMelWarps * 32, 0, st>>>(h, (int)ldh, window,
                                                                        frames_scratch, rows);
   istft_ola_kernel<<<dim3(cdiv(out_len, 256), batch), 256, 0, st>>>(frames_scratch, window, frames,

@@ -15,6 +15,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                                        S::kTotal));
     attr_set = true;
   }
+  const double taps = p.conv_taps;
+  ProfScope ps(PROF_GEMM, 2.0 * p.M * (double)p.N * (double)p.k_per_tap * taps,
+               2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
+                   (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
+               stream);
   kern<<<grid, 192, S::kTotal, stream>>>(ta, tb, p);
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;

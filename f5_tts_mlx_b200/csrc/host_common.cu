@@ -1,6 +1,8 @@
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace f5 {
 
@@ -80,9 +82,59 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ---------------------------------------------------------------------------------------------
+struct ProfRec { int kind; double flops, bytes; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::atomic<long long> g_launches{0};
+
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st) : idx_(-1), st_(st) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.kind = kind; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  idx_ = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[idx_].e1, st_);
+}
+
 }  // namespace f5
 
 extern "C" {
+long long f5_launch_count(void) { return f5::g_launches.load(); }
+int f5_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(f5::g_prof_mu);
+  for (auto& r : f5::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  f5::g_prof.clear();
+  f5::g_prof_on = on != 0;
+  return 0;
+}
+// out: [kinds][4] = {milliseconds, flops, bytes, launches}
+int f5_prof_summary(double* out, int kinds) {
+  std::lock_guard<std::mutex> lk(f5::g_prof_mu);
+  for (int i = 0; i < kinds * 4; ++i) out[i] = 0.0;
+  for (auto& r : f5::g_prof) {
+    if (r.kind >= kinds) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return f5::set_error(F5_ERR_CUDA, "prof: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    out[r.kind * 4 + 0] += ms;
+    out[r.kind * 4 + 1] += r.flops;
+    out[r.kind * 4 + 2] += r.bytes;
+    out[r.kind * 4 + 3] += 1.0;
+  }
+  return 0;
+}
 const char* f5_last_error(void) { return f5::g_err; }
 int f5_abi_version(void) { return 1000; }
 int f5_device_check(void) { return f5::device_check(); }

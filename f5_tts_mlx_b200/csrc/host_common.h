@@ -36,4 +36,16 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- launch accounting + optional per-kernel-family device timing (bench.py roofline) ----
+// Every launcher opens a ProfScope around its kernel launch.  The launch counter is always on;
+// when profiling is enabled (f5_prof_enable) a CUDA event pair brackets the launch on its stream
+// and f5_prof_summary returns the summed device time / algorithmic FLOPs / bytes per family.
+enum ProfKind { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NKINDS = 4 };
+struct ProfScope {
+  ProfScope(int kind, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t st_;
+};
+
 }  // namespace f5

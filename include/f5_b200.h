@@ -38,6 +38,13 @@ const char* f5_last_error(void);
 /* library/ABI version (major*1000+minor) and the device check used by every entry point */
 int f5_abi_version(void);
 int f5_device_check(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+long long f5_launch_count(void);
+/* optional per-kernel-family device timing: enable, run, then read
+ * out[kinds][4] = {milliseconds, algorithmic flops, bytes, launches}; kinds: 0 GEMM, 1 attention,
+ * 2 LayerNorm+modulate, 3 everything else. */
+int f5_prof_enable(int on);
+int f5_prof_summary(double* out, int kinds);
 
 /* ------------------------------------------------------------------------------------------ *
  * Dense / implicit-conv GEMM on tcgen05 tensor cores:  out = epilogue(A · W^T)
