@@ -219,6 +219,13 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.profile_run:
+        # under ncu: one eager pass of the same step (no graph, no e2e, no CPU leg), nothing is timed
+        f5.use_cuda_graph = False
+        f5.sample(cond_d, text, N, y0=y0_d, **kw)
+        torch.cuda.synchronize()
+        return
+
     # ---- warm-up (also captures the CUDA graph) ----
     for _ in range(max(args.warmup, 3)):
         out, _ = f5.sample(cond_d, text, N, y0=y0_d, **kw)
@@ -343,6 +350,7 @@ def main():
     ap.add_argument("--method", default="euler", choices=["euler", "midpoint", "rk4"])
     ap.add_argument("--cfg", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="one eager step and exit (for ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -66,6 +66,7 @@ SYMBOLS: dict[str, tuple] = {
     "f5_last_error": (C.c_char_p, []),
     "f5_abi_version": (C.c_int, []),
     "f5_device_check": (C.c_int, []),
+    "f5_struct_sizes": (C.c_int, [C.POINTER(C.c_int32), C.c_int32]),
     "f5_launch_count": (C.c_longlong, []),
     "f5_prof_enable": (C.c_int, [C.c_int]),
     "f5_prof_summary": (C.c_int, [C.POINTER(C.c_double), C.c_int]),

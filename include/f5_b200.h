@@ -43,6 +43,10 @@ long long f5_launch_count(void);
 /* optional per-kernel-family device timing: enable, run, then read
  * out[kinds][4] = {milliseconds, algorithmic flops, bytes, launches}; kinds: 0 GEMM, 1 attention,
  * 2 LayerNorm+modulate, 3 everything else. */
+/* sizeof() of the ABI structs in declaration order: f5_gemm_args, f5_convnext_weights,
+ * f5_dit_block_weights, f5_dit_weights, f5_dit_buffers, f5_vocos_block_weights, f5_vocos_weights,
+ * f5_vocos_buffers — lets a binding check its layout at load time.  Returns the count (8). */
+int f5_struct_sizes(int32_t* out, int32_t n);
 int f5_prof_enable(int on);
 int f5_prof_summary(double* out, int kinds);
 

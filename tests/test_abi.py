@@ -1,0 +1,80 @@
+"""The C-ABI library loads, exports every symbol include/f5_b200.h declares, its struct layouts
+match the ctypes mirrors, and — on a box without a GPU — every compute entry point fails loudly
+instead of falling back to a CPU path.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from f5_tts_mlx_b200 import _lib
+from f5_tts_mlx_b200.dit import DitBuffersC
+from f5_tts_mlx_b200.vocos import VocosBlockWeightsC, VocosBuffersC, VocosWeightsC
+from f5_tts_mlx_b200.weights import ConvNextWeightsC, DitBlockWeightsC, DitWeightsC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "f5_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(f5_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/f5_b200.h but not exported by libf5b200.so"
+        assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype in _lib.SYMBOLS"
+    for n in _lib.SYMBOLS:
+        assert n in names, f"{n} bound in _lib.py but not declared in the header"
+
+
+def test_struct_layouts_match_ctypes():
+    lib = _lib.load()
+    out = (C.c_int32 * 8)()
+    assert lib.f5_struct_sizes(out, 8) == 8
+    mirrors = [_lib.GemmArgs, ConvNextWeightsC, DitBlockWeightsC, DitWeightsC, DitBuffersC, VocosBlockWeightsC,
+               VocosWeightsC, VocosBuffersC]
+    for got, m in zip(list(out), mirrors):
+        assert got == C.sizeof(m), f"{m.__name__}: C sizeof {got} != ctypes {C.sizeof(m)}"
+
+
+def test_abi_version():
+    assert _lib.load().f5_abi_version() >= 1000
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_entry_points_fail_loudly():
+    lib = _lib.load()
+    assert lib.f5_device_check() == -3                     # F5_ERR_NO_DEVICE
+    g = _lib.GemmArgs()
+    assert lib.f5_gemm_bf16(C.byref(g), None) == -3
+    assert b"no CPU fallback" in lib.f5_last_error() or b"sm_100a" in lib.f5_last_error()
+    assert lib.f5_attention_fwd(None, 0, None, 0, 1, 1, 1, 64, None, None) == -3
+    assert lib.f5_dit_forward(None, None, 0, None) == -3
+    assert lib.f5_mel_forward(None, 1, 1, None, None, 100, 256, None, 1, None) == -3
+    assert lib.f5_vocos_decode(None, None, None, None, None) == -3
+    with pytest.raises(_lib.F5Error):
+        _lib.check(lib.f5_device_check())
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_python_surface_refuses_cpu_tensors():
+    from f5_tts_mlx_b200 import MelSpec
+    with pytest.raises(_lib.F5Error):
+        MelSpec()(torch.zeros(2048))
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: the product path must not route through it."""
+    pkg = os.path.join(ROOT, "f5_tts_mlx_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle)", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not pat.search(src), f"{fn} imports the oracle"

@@ -1,0 +1,259 @@
+"""-m gpu: the parity tests proper — CUDA path (through the C ABI and the reference-shaped Python
+surface) vs the CPU oracle on the same seeded inputs, vs the committed golden fixtures, and
+size-independent properties at the full BASELINE sizes.
+
+Tolerance (derived, not guessed — see tests/test_oracle_pins.py::test_sample_golden_and_bf16_drift):
+the oracle with bf16-rounded tensor-core operands drifts 1e-3 .. 4e-3 (rel. L2) from the fp32
+oracle on these configs; the CUDA path must stay within 3x that measured drift (and an absolute
+cap of 2e-2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import f5_oracle as O
+from helpers import make_dit, ocfg_of, rel, synth_audio
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+@pytest.fixture(scope="module")
+def gate():
+    from f5_tts_mlx_b200.weights import GATE_CONFIG, random_dit_weights
+    W = random_dit_weights(GATE_CONFIG, seed=1234)
+    return GATE_CONFIG, W, make_dit(GATE_CONFIG, W)
+
+
+def within_drift(got, ref_fp32, ref_bf16emu, factor=3.0, cap=2e-2):
+    drift = rel(ref_bf16emu, ref_fp32)
+    r = rel(got, ref_fp32)
+    assert torch.isfinite(got).all()
+    assert r < min(max(factor * drift, 2e-3), cap), f"rel {r:.3e} vs drift {drift:.3e}"
+    return r, drift
+
+
+# ---------------- DiT forward ----------------
+def test_dit_forward_golden_fixture(gate, golden_dir):
+    cfg, W, model = gate
+    z = np.load(os.path.join(golden_dir, "dit_gate_forward.npz"))
+    lens = torch.from_numpy(z["lens"]); N = z["x"].shape[1]
+    mask = (torch.arange(N)[None] < lens[:, None]).to(dev)
+    args = (torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["cond"]).to(dev), torch.from_numpy(z["text"]).to(dev),
+            torch.tensor(float(z["t"])))
+    out = model(*args, False, False, mask).cpu()
+    assert rel(out, torch.from_numpy(z["out"])) < 1e-2
+    out_d = model(*args, True, True, mask).cpu()
+    assert rel(out_d, torch.from_numpy(z["out_drop"])) < 1e-2
+
+
+@pytest.mark.parametrize("B,N,nt,drops,lens", [(1, 200, 40, (False, False), None), (1, 200, 40, (True, False), None),
+                                               (1, 130, 300, (False, True), None), (2, 300, 60, (False, False), [300, 211]),
+                                               (1, 5, 3, (False, False), None)])
+def test_dit_forward_vs_oracle(gate, B, N, nt, drops, lens):
+    cfg, W, model = gate
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, 100, generator=g); cond = torch.randn(B, N, 100, generator=g) * 2 - 1
+    text = torch.randint(0, 2545, (B, nt), generator=g, dtype=torch.int32)
+    if B > 1:
+        text[1, nt - 17:] = -1
+    t = torch.tensor(0.37)
+    mask = (torch.arange(N)[None] < torch.tensor(lens)[:, None]) if lens is not None else None
+    ref = O.dit_forward(x, cond, text, t, drops[0], drops[1], mask, W, ocfg_of(cfg))
+    ref16 = O.dit_forward(x, cond, text, t, drops[0], drops[1], mask, W, ocfg_of(cfg), O.Precision(True))
+    got = model(x.to(dev), cond.to(dev), text.to(dev), t, drops[0], drops[1], mask.to(dev) if mask is not None else None).cpu()
+    within_drift(got, ref, ref16)
+
+
+# ---------------- sample(): BASELINE config 1 (the numerics gate) and the other solvers ----------------
+def test_sample_config1_numerics_gate(gate):
+    """BASELINE.json configs[0]: single 10 s utterance (937 frames), 4-layer/512-dim DiT random-init,
+    Euler, steps=8 grid points, CFG 2, sway -1 — (out mel, trajectory[-1]) vs the CPU oracle."""
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = gate
+    g = torch.Generator().manual_seed(1)
+    N, nref = 937, 328
+    cond = (torch.randn(1, nref, 100, generator=g) * 2.24 - 1.27).clamp(-11.51, 5)
+    text = torch.randint(0, 2545, (1, 152), generator=g, dtype=torch.int32)
+    y0 = torch.randn(1, 100, N, generator=g).permute(0, 2, 1).contiguous()
+    kw = dict(steps=8, method="euler", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    ref, ref_traj = O.sample(cond, text, N, W, ocfg_of(cfg), **kw)
+    ref16, _ = O.sample(cond, text, N, W, ocfg_of(cfg), prec=O.Precision(True), **kw)
+    f5 = F5TTS(model)
+    for graph in (False, True):
+        f5.use_cuda_graph = graph
+        out, traj = f5.sample(cond.to(dev), text, N, **kw)
+        assert traj.shape == ref_traj.shape == (8, 1, N, 100)
+        r, drift = within_drift(out.cpu(), ref, ref16)
+        assert rel(traj[-1].cpu(), ref_traj[-1]) < 3 * max(drift, 1e-3)
+        assert (out.cpu() - ref).abs().max().item() < 5e-2               # log-mel units
+        assert torch.equal(out[0, :nref].cpu(), cond[0])                  # ref frames written back (cfm.py:395-397)
+    # replaying the captured graph with new noise gives the new answer, not the cached one
+    y1 = torch.randn(1, 100, N, generator=g).permute(0, 2, 1).contiguous()
+    out1, _ = f5.sample(cond.to(dev), text, N, **{**kw, "y0": y1})
+    ref1, _ = O.sample(cond, text, N, W, ocfg_of(cfg), **{**kw, "y0": y1})
+    assert rel(out1.cpu(), ref1) < 1e-2
+
+
+def test_sample_golden_fixture_all_solvers(gate, golden_dir):
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = gate
+    z = np.load(os.path.join(golden_dir, "sample_gate.npz"))
+    cond, text, y0, N = torch.from_numpy(z["cond"]), torch.from_numpy(z["text"]), torch.from_numpy(z["y0"]), int(z["duration"])
+    f5 = F5TTS(model)
+    out, traj = f5.sample(cond.to(dev), text, N, steps=4, method="euler", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    assert rel(out.cpu(), torch.from_numpy(z["euler_out"])) < 1e-2
+    assert rel(traj[-1].cpu(), torch.from_numpy(z["euler_traj_last"])) < 1e-2
+    out, _ = f5.sample(cond.to(dev), text, N, steps=3, method="midpoint", cfg_strength=0.0, sway_sampling_coef=None, y0=y0)
+    assert rel(out.cpu(), torch.from_numpy(z["midpoint_nocfg_out"])) < 1e-2
+    out, _ = f5.sample(cond.to(dev), text, N, steps=3, method="rk4", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    assert rel(out.cpu(), torch.from_numpy(z["rk4_out"])) < 1e-2
+
+
+def test_sample_ragged_batch_and_text_longer_than_audio(gate):
+    """batch > 1 => key-padding mask + zeroed padded query rows (dit.py:161-173), per-utterance
+    durations, lens = max(text_len, cond_len) (cfm.py:301-303)."""
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = gate
+    g = torch.Generator().manual_seed(5)
+    cond = (torch.randn(2, 50, 100, generator=g) * 2.24 - 1.27)
+    text = torch.randint(0, 2545, (2, 60), generator=g, dtype=torch.int32); text[1, 20:] = -1
+    dur = torch.tensor([120, 90])
+    y0 = torch.randn(2, 120, 100, generator=g); y0[1, 90:] = 0
+    kw = dict(steps=3, method="midpoint", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    ref, _ = O.sample(cond, text, dur, W, ocfg_of(cfg), **kw)
+    ref16, _ = O.sample(cond, text, dur, W, ocfg_of(cfg), prec=O.Precision(True), **kw)
+    out, traj = F5TTS(model).sample(cond.to(dev), text, dur, **kw)
+    assert out.shape == ref.shape == (2, 120, 100)
+    within_drift(out.cpu(), ref, ref16)
+
+
+def test_sample_seeded_noise_is_deterministic_and_same_per_element(gate):
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = gate
+    cond = torch.randn(2, 30, 100).to(dev)
+    text = torch.randint(0, 100, (2, 10), dtype=torch.int32)
+    f5 = F5TTS(model)
+    a, ta = f5.sample(cond, text, 64, steps=2, method="euler", seed=3)
+    b, tb = f5.sample(cond, text, 64, steps=2, method="euler", seed=3)
+    assert torch.equal(a, b)
+    assert torch.equal(ta[0, 0], ta[0, 1])            # same seed re-applied per element (cfm.py:371-373)
+
+
+# ---------------- full-size properties: BASELINE configs 2-3 shapes on the base model ----------------
+@pytest.fixture(scope="module")
+def base():
+    from f5_tts_mlx_b200.weights import BASE_CONFIG, random_dit_weights
+    W = random_dit_weights(BASE_CONFIG, seed=1234)
+    return BASE_CONFIG, W, make_dit(BASE_CONFIG, W)
+
+
+def test_base_model_single_forward_vs_oracle(base):
+    """One full-size DiT evaluation (22 layers, 1024-dim, N = 937) against the oracle (a few CPU seconds)."""
+    cfg, W, model = base
+    g = torch.Generator().manual_seed(2)
+    N = 937
+    x = torch.randn(1, N, 100, generator=g); cond = (torch.randn(1, N, 100, generator=g) * 2.24 - 1.27); cond[:, 328:] = 0
+    text = torch.randint(0, 2545, (1, 152), generator=g, dtype=torch.int32)
+    t = torch.tensor(0.25)
+    ref = O.dit_forward(x, cond, text, t, False, False, None, W, ocfg_of(cfg))
+    ref16 = O.dit_forward(x, cond, text, t, False, False, None, W, ocfg_of(cfg), O.Precision(True))
+    got = model(x.to(dev), cond.to(dev), text.to(dev), t).cpu()
+    within_drift(got, ref, ref16)
+
+
+def test_base_model_batched_cfg_equals_two_unbatched_passes_and_batch_invariance(base):
+    """Properties that need no oracle at full size: (1) the doubled-batch CFG step equals
+    pred + (pred - null) * cfg from two separate forwards (cfm.py:342-364); (2) an utterance gives
+    the same result alone and inside a batch of identical utterances (no cross-utterance coupling)."""
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = base
+    g = torch.Generator().manual_seed(3)
+    N, nref = 937, 328
+    cond = (torch.randn(1, nref, 100, generator=g) * 2.24 - 1.27).clamp(-11.51, 5).to(dev)
+    text = torch.randint(0, 2545, (1, 152), generator=g, dtype=torch.int32)
+    y0 = torch.randn(1, N, 100, generator=g).to(dev)
+    f5 = F5TTS(model)
+    out, traj = f5.sample(cond, text, N, steps=2, method="euler", cfg_strength=2.0, sway_sampling_coef=None, y0=y0)
+    step_cond = torch.zeros(1, N, 100, device=dev); step_cond[:, :nref] = cond
+    t0 = torch.tensor(0.0)
+    pred = model(y0, step_cond, text.to(dev), t0, False, False)
+    null = model(y0, step_cond, text.to(dev), t0, True, True)
+    y1 = y0 + 1.0 * (pred + (pred - null) * 2.0)
+    assert rel(traj[-1], y1) < 1e-5
+    cond3, text3, y03 = cond.repeat(3, 1, 1), text.repeat(3, 1), y0.repeat(3, 1, 1)
+    out3, _ = f5.sample(cond3, text3, N, steps=2, method="euler", cfg_strength=2.0, sway_sampling_coef=None, y0=y03)
+    assert rel(out3[1], out[0]) < 1e-5 and torch.equal(out3[0], out3[2])
+
+
+def test_base_model_long_form_60s_runs_and_is_finite(base):
+    """BASELINE configs[4] shape: N = 5625 frames (60 s), max_duration passed explicitly; text positions
+    beyond 4095 reuse the last table row (rope.py:83)."""
+    from f5_tts_mlx_b200 import F5TTS
+    cfg, W, model = base
+    g = torch.Generator().manual_seed(4)
+    cond = (torch.randn(1, 499, 100, generator=g) * 2.24 - 1.27).to(dev)
+    text = torch.randint(0, 2545, (1, 900), generator=g, dtype=torch.int32)
+    out, traj = F5TTS(model).sample(cond, text, 5625, steps=3, method="euler", cfg_strength=2.0, seed=0, max_duration=8192,
+                                    return_trajectory=False)
+    assert out.shape == (1, 5625, 100) and torch.isfinite(out).all()
+    capped, _ = F5TTS(model).sample(cond, text, 5625, steps=2, method="euler", cfg_strength=0.0, seed=0, return_trajectory=False)
+    assert capped.shape == (1, 4096, 100)             # default max_duration = 4096 (cfm.py:277,318)
+
+
+# ---------------- audio front-end / vocoder ----------------
+def test_mel_golden_fixture_and_oracle(golden_dir):
+    from f5_tts_mlx_b200 import MelSpec
+    z = np.load(os.path.join(golden_dir, "mel_fixture.npz"))
+    x = torch.from_numpy(z["pcm"].astype(np.float32) / 32768.0)
+    got = MelSpec()(x.to(dev)).cpu()[0]
+    assert got.shape == (93, 100) and (got - torch.from_numpy(z["mel"])).abs().max().item() < 2e-3
+    for L in (240000, 127985, 1024, 700, 256):
+        a = synth_audio(L, seed=L)
+        got, ref = MelSpec()(a.to(dev)).cpu(), O.log_mel_spectrogram(a)
+        assert got.shape == ref.shape == (1, L // 256, 100)
+        assert (got - ref).abs().max().item() < 3e-3
+    xb = torch.stack([synth_audio(24000, 1), synth_audio(24000, 2)])
+    assert (MelSpec()(xb.to(dev)).cpu() - O.log_mel_spectrogram(xb)).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("norm,trim", [("window", False), ("window_sq", True)])
+def test_vocos_vs_oracle_and_golden(golden_dir, norm, trim):
+    from f5_tts_mlx_b200.vocos import Vocos
+    from f5_tts_mlx_b200.weights import VocosConfig, random_vocos_weights
+    vc, ovc = VocosConfig(istft_norm=norm, istft_trim=trim), O.VocosConfig(istft_norm=norm, istft_trim=trim)
+    vw = random_vocos_weights(vc, seed=4321)
+    voc = Vocos(vc, dev).load_weights(vw)
+    z = np.load(os.path.join(golden_dir, "vocos_small.npz"))
+    got = voc.decode(torch.from_numpy(z["mel"]).to(dev)).cpu()
+    gold = torch.from_numpy(z["wave_window" if norm == "window" else "wave_window_sq_trim"])
+    assert got.shape == gold.shape and rel(got, gold) < 2e-2
+    for n in (2, 499, 937):
+        mel = (torch.randn(1, n, 100) * 2.24 - 1.27).clamp(-11.5, 5)
+        ref, ref16 = O.vocos_decode(mel, vw, ovc), O.vocos_decode(mel, vw, ovc, O.Precision(True))
+        got = voc.decode(mel.to(dev)).cpu()
+        assert got.shape == ref.shape
+        within_drift(got, ref, ref16)
+        snr = 10 * torch.log10(ref.pow(2).sum() / (got - ref).pow(2).sum()).item()
+        assert snr > 40.0, f"SNR {snr:.1f} dB"
+
+
+def test_end_to_end_raw_wave_to_waveform(gate):
+    """sample(raw wave, text) with a vocoder: mel front-end -> ODE -> Vocos, output is a 1-D wave whose
+    first len(audio) samples are the re-synthesised reference (generate.py:183 strips them)."""
+    from f5_tts_mlx_b200 import F5TTS
+    from f5_tts_mlx_b200.vocos import Vocos
+    from f5_tts_mlx_b200.weights import VocosConfig, random_vocos_weights
+    cfg, W, model = gate
+    vw = random_vocos_weights()
+    voc = Vocos(VocosConfig(), dev).load_weights(vw)
+    audio = synth_audio(256 * 80, 9)
+    text = torch.randint(0, 2545, (1, 30), dtype=torch.int32)
+    N = 200
+    y0 = torch.randn(1, N, 100)
+    kw = dict(steps=3, method="euler", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    wave, traj = F5TTS(model, vocoder=voc.decode).sample(audio[None].to(dev), text, N, **kw)
+    ref, _ = O.sample(audio[None], text, N, W, ocfg_of(cfg), vocoder=lambda m: O.vocos_decode(m, vw), **kw)
+    assert wave.ndim == 1 and wave.shape == ref.shape == ((N - 1) * 256 + 1024,)
+    assert rel(wave.cpu(), ref) < 3e-2
