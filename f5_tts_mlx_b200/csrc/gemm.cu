@@ -1,5 +1,6 @@
 // Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm_sm100.cuh and include/f5_b200.h).
 #include "gemm_sm100.cuh"
+#include "gemm2_sm100.cuh"
 #include "host_common.h"
 
 namespace f5 {
@@ -43,6 +44,53 @@ static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta
                    act, (int)out_bf16, (int)rope);
 }
 
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                        int n_tiles, int total_tiles, cudaStream_t stream) {
+  using S = Gemm2Smem<BN, kStages>;
+  auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    F5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       S::kTotal));
+    attr_set = true;
+  }
+  static int num_pairs = 0;
+  if (num_pairs == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    num_pairs = sms / 2;
+  }
+  const int clusters = total_tiles < num_pairs ? total_tiles : num_pairs;
+  const double taps = p.conv_taps;
+  ProfScope ps(PROF_GEMM, 2.0 * p.M * (double)p.N * (double)p.k_per_tap * taps,
+               2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
+                   (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
+               stream);
+  kern<<<2 * clusters, 256, S::kTotal, stream>>>(ta, tb, p, n_tiles, total_tiles);
+  F5_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN, int kStages>
+static int dispatch_epi2(int act, bool out_bf16, bool rope, const CUtensorMap& ta,
+                         const CUtensorMap& tb, const GemmParams& p, int n_tiles, int total_tiles,
+                         cudaStream_t stream) {
+#define F5_CASE(A, O, R) \
+  if (act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R>(ta, tb, p, n_tiles, total_tiles, stream);
+  F5_CASE(ACT_NONE, true, true)
+  F5_CASE(ACT_NONE, true, false)
+  F5_CASE(ACT_NONE, false, false)
+  F5_CASE(ACT_GELU_TANH, true, false)
+  F5_CASE(ACT_GELU_ERF, true, false)
+  F5_CASE(ACT_MISH, true, false)
+  F5_CASE(ACT_MISH, false, false)
+#undef F5_CASE
+  return set_error(F5_ERR_INVALID, "f5_gemm_bf16: unsupported epilogue act=%d out_bf16=%d rope=%d",
+                   act, (int)out_bf16, (int)rope);
+}
+
 }  // namespace f5
 
 extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
@@ -69,6 +117,57 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
   }
   if (a->resid) F5_REQUIRE(a->ldr % 4 == 0, "f5_gemm_bf16: ldr not multiple of 4");
   if (a->gate) F5_REQUIRE(a->gate_ld % 4 == 0, "f5_gemm_bf16: gate_ld not multiple of 4");
+
+  int variant = a->variant;
+  if (a->conv_grouped) variant = 1;            // grouped conv: 64-wide column blocks, single-CTA kernel
+  if (variant == 0) {
+    // measured on B200 (tests/gpu_checks/check_gemm2.py): the persistent CTA-pair kernel with 256-wide
+    // tiles wins whenever there are enough 256x256 tiles to fill the 74 SM pairs (large M: 1.2-1.35
+    // PFLOP/s vs 0.85-1.0), and for wide outputs (N >= 3072) even at M ~ 2k; the single-CTA kernel
+    // with 128x128 tiles spreads small problems over more SMs.
+    const long long pair_tiles = (long long)cdiv(a->m, 256) * cdiv(a->n, 256);
+    variant = (a->n >= 128 && (pair_tiles >= 148 || (pair_tiles >= 74 && a->n >= 3072))) ? 2 : 1;
+  }
+  if (variant == 2) {
+    int bn2 = a->tile_n;
+    if (bn2 == 0) bn2 = (a->n % 256 == 0 || a->n >= 1024) ? 256 : 128;
+    F5_REQUIRE(bn2 == 128 || bn2 == 256, "f5_gemm_bf16: CTA-pair tile_n must be 128 or 256");
+    GemmParams p2;
+    p2.M = a->m; p2.N = a->n; p2.K = a->k;
+    p2.rows_per_batch = rpb;
+    p2.tiles_per_batch = batched ? cdiv(rpb, 256) : 0;
+    p2.num_batches = nb;
+    p2.conv_taps = taps; p2.conv_pad = a->conv_pad; p2.k_per_tap = a->k; p2.conv_grouped = 0;
+    p2.bias = a->bias; p2.out = a->out; p2.ldo = (int)a->ldo;
+    p2.resid = a->resid; p2.ldr = (int)a->ldr;
+    p2.gate = a->gate; p2.gate_ld = (int)a->gate_ld;
+    p2.row_len = a->row_len;
+    p2.rope = reinterpret_cast<const float2*>(a->rope);
+    p2.rope_cols = a->rope_cols; p2.q_scale = a->q_scale; p2.q_cols = a->q_cols;
+    p2.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p2.ldo2 = (int)a->ldo2;
+    if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
+    CUtensorMap ta2, tb2;
+    {
+      uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)(batched ? rpb : a->m), (uint64_t)(batched ? nb : 1)};
+      uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * (uint64_t)rpb};
+      uint32_t box[3] = {64, 128, 1};
+      if (int e = make_tmap_bf16(&ta2, a->a, 3, dims, str, box)) return e;
+    }
+    {
+      const int kpad = cdiv(a->k, 64) * 64;
+      uint64_t dims[2] = {(uint64_t)(taps == 1 ? a->k : taps * kpad), (uint64_t)a->n};
+      uint64_t str[1] = {(uint64_t)a->ldw * 2};
+      uint32_t box[2] = {64, (uint32_t)(bn2 / 2)};
+      if (int e = make_tmap_bf16(&tb2, a->w, 2, dims, str, box)) return e;
+    }
+    const int n_tiles = cdiv(a->n, bn2);
+    const int m_tiles = batched ? nb * cdiv(rpb, 256) : cdiv(a->m, 256);
+    cudaStream_t stream2 = reinterpret_cast<cudaStream_t>(stream_);
+    const bool rope2 = a->rope != nullptr;
+    if (bn2 == 256)
+      return dispatch_epi2<256, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+    return dispatch_epi2<128, 8>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+  }
 
   int bn = a->tile_n;
   if (a->conv_grouped) bn = 64;

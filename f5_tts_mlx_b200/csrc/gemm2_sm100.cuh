@@ -1,0 +1,258 @@
+// Persistent 2-CTA (cta_group::2) tcgen05 GEMM for sm_100a — the large-problem variant of
+// gemm_sm100.cuh (same math, same fused epilogue, same implicit-conv mode).
+//
+// A cluster of two CTAs (one SM pair / TPC) computes 256 x BN output tiles with ONE
+// `tcgen05.mma.cta_group::2` stream issued by the leader CTA: CTA r holds rows [128r, 128r+128) of
+// A and HALF of the B tile (BN/2 weight rows) in its shared memory, the tensor cores of both SMs
+// read both halves, and each CTA's TMEM receives its 128 accumulator rows.  Per k-block a CTA
+// pulls 16 KB (A) + BN/2*128 B (B) through L2 for 128 x BN x 64 MACs — twice the arithmetic
+// intensity of the single-CTA 128 x 128 tile, which is what lifts the L2->SM bandwidth cap.
+//
+// Persistent: grid = min(74 clusters, tiles); tiles are walked n-fastest.  Warp roles (256 threads):
+//   warp 0  TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
+//   warp 1  MMA issuer (leader only); tcgen05.commit multicast frees the stage in both CTAs
+//   warp 2  TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7 epilogue (both CTAs): drains accumulator stage i while the MMAs fill stage i^1,
+//           then arrives on the leader's tmem_empty barrier
+#pragma once
+#include "gemm_epilogue.cuh"
+
+namespace f5 {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (count 1) on the barrier at the same smem offset in every CTA of `mask` when all prior
+// tcgen05.mma of this thread have completed
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(
+                   smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+
+template <int BN, int kStages>
+struct Gemm2Smem {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = (BN / 2) * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;  // + align slack
+};
+
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
+                     const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
+                     const int n_tiles, const int total_tiles) {
+  using S = Gemm2Smem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2] (leader's copy is the live one)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int kb_per_tap = (p.k_per_tap + 63) >> 6;
+  const int num_kb = p.conv_taps * kb_per_tap;
+  const int pair_tiles_per_batch = p.tiles_per_batch;   // in units of 256-row pair tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int kcount = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        const int n_tile = t % n_tiles, m_tile = t / n_tiles;
+        const int n0 = n_tile * BN;
+        int batch = 0, m_in_batch0;
+        if (pair_tiles_per_batch > 0) {
+          batch = m_tile / pair_tiles_per_batch;
+          m_in_batch0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
+        } else {
+          m_in_batch0 = m_tile * 256 + (int)rank * 128;
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
+          const int s = kcount % kStages;
+          const uint32_t ph = (kcount / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          const int tap = kb / kb_per_tap;
+          const int kc = kb - tap * kb_per_tap;
+          const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
+          tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
+          tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * 64, n0 + (int)rank * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      int kcount = 0, acount = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acount) {
+        const int as = acount & 1;
+        const uint32_t aph = (acount >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
+          const int s = kcount % kStages;
+          const uint32_t ph = (kcount / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+            const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+              uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+              umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+            }
+            tc_commit_2sm(&empty_bar[s], 3);
+            if (kb == num_kb - 1) tc_commit_2sm(&tmem_full_bar[as], 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int lg = warp & 3;
+    const int r_in_tile = (int)rank * 128 + lg * 32 + lane;   // row inside the 256-row pair tile
+    int acount = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acount) {
+      const int n_tile = t % n_tiles, m_tile = t / n_tiles;
+      const int n0 = n_tile * BN;
+      const int as = acount & 1;
+      const uint32_t aph = (acount >> 1) & 1;
+      int row, pos, b_idx;
+      bool row_ok;
+      if (pair_tiles_per_batch > 0) {
+        b_idx = m_tile / pair_tiles_per_batch;
+        pos = (m_tile % pair_tiles_per_batch) * 256 + r_in_tile;
+        row_ok = pos < p.rows_per_batch;
+        row = b_idx * p.rows_per_batch + pos;
+      } else {
+        row = m_tile * 256 + r_in_tile;
+        row_ok = row < p.M;
+        const int rpb = p.rows_per_batch > 0 ? p.rows_per_batch : p.M;
+        b_idx = row / rpb;
+        pos = row - b_idx * rpb;
+      }
+      if (!row_ok) { b_idx = 0; pos = 0; }
+      bool row_valid = true;
+      if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
+
+      mbar_wait(&tmem_full_bar[as], aph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tmem_acc + c * 32, acc);
+        tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) continue;
+        gemm_epilogue_chunk<ACT, OUT_BF16, ROPE>(acc, p, col0, row, pos, b_idx, row_ok, row_valid);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace f5

@@ -53,6 +53,7 @@ def gemm(
     conv_pad: int = 0,
     conv_grouped: bool = False,
     tile_n: int = 0,
+    variant: int = 0,
 ) -> torch.Tensor:
     _need_cuda(a, w, out, bias, resid, gate, row_len, rope)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -87,5 +88,6 @@ def gemm(
         g.rope = rope.data_ptr()
     g.rope_cols, g.q_scale, g.q_cols = rope_cols, q_scale, q_cols
     g.tile_n = tile_n
+    g.variant = variant
     _lib.check(_lib.load().f5_gemm_bf16(C.byref(g), _stream()))
     return out

@@ -90,9 +90,11 @@ typedef struct f5_gemm_args {
   int32_t rope_cols;      /* columns [0, rope_cols) are rotated in adjacent pairs               */
   float q_scale;          /* columns [0, q_cols) are multiplied by q_scale after the rotation   */
   int32_t q_cols;
-  int32_t tile_n;         /* 0 = auto, else 64 | 128                                            */
+  int32_t tile_n;         /* 0 = auto, else 64 | 128 (single-CTA kernel), 128 | 256 (CTA-pair)   */
   void* out2_bf16;        /* optional second copy of the result as bf16 [rows, ldo2], or NULL    */
   int64_t ldo2;
+  int32_t variant;        /* 0 auto | 1 single-CTA 128xBN tiles | 2 persistent CTA-pair 256xBN    */
+  int32_t reserved;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
