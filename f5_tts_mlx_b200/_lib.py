@@ -59,6 +59,7 @@ class GemmArgs(C.Structure):
         ("tile_n", C.c_int32),
         ("out2_bf16", C.c_void_p), ("ldo2", C.c_int64),
         ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("debug_ts", C.c_void_p),
     ]
 
 

@@ -1,5 +1,8 @@
 // Host launcher + C-ABI entry for the tcgen05 flash-attention forward (attention_sm100.cuh).
+#include <stdlib.h>
+
 #include "attention_sm100.cuh"
+#include "attention2_sm100.cuh"
 #include "host_common.h"
 
 extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
@@ -23,15 +26,28 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ld_out;
   static bool attr_set = false;
+  static int variant = 2;   // 2: two query tiles per CTA, O in TMEM (attention2_sm100.cuh); 1: v1
   if (!attr_set) {
     F5_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        AttnSmem::kTotal));
+    F5_CHECK_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Attn2Smem::kTotal));
+    const char* v = getenv("F5_ATTN_VARIANT");
+    if (v && v[0] == '1') variant = 1;
     attr_set = true;
+  }
+  if (variant == 2) {
+    dim3 grid2(cdiv(frames, 256), heads, batch);
+    ProfScope ps2(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
+                  2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
+    F5_CHECK_CUDA(launch_kernel(attn2_fwd_kernel, dim3(grid2), dim3(384), Attn2Smem::kTotal, reinterpret_cast<cudaStream_t>(stream_), tm, p));
+    F5_CHECK_CUDA(cudaGetLastError());
+    return 0;
   }
   dim3 grid(cdiv(frames, 128), heads, batch);
   ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
                2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
-  attn_fwd_kernel<<<grid, 192, AttnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream_)>>>(tm, p);
+  F5_CHECK_CUDA(launch_kernel(attn_fwd_kernel, dim3(grid), dim3(192), AttnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream_), tm, p));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,285 @@
+// Flash-attention forward v2 for sm_100a (head_dim 64, non-causal, key-padding mask): two 128-query
+// tiles per CTA ping-pong on one tensor-core stream, accumulator O kept in TMEM with lazy rescaling.
+// Same contract as attention_sm100.cuh (replaces mx.fast.scaled_dot_product_attention, dit.py:166).
+//
+//   warp 0      TMA: Q0,Q1 once; K/V 128-key tiles in 2-stage rings
+//   warp 1      MMA issuer, order  S0_0 S1_0 | PV0_j S0_{j+1} PV1_j S1_{j+1} | ...
+//               S_g = Q_g K^T (M128 N128 K64) -> TMEM S_g;  O_g += P_g V (M128 N64 K128) -> TMEM O_g
+//   warps 2-3   idle (complete warpgroup 0, which hands its registers to the softmax warpgroups)
+//   warps 4-7   softmax group 0 (thread = query row of tile 0), 224 registers via setmaxnreg
+//   warps 8-11  softmax group 1 (tile 1)
+// While group 0 exponentiates S0_j the tensor cores compute S1_j / PV1_{j-1}, and vice versa.
+// The running max used for exponentiation (m_used) is only advanced — and O_g/l rescaled in TMEM —
+// when the true row max has grown by more than 2^8 (any thread of the warp), so the common case
+// has no accumulator traffic at all; the final O/l is exact either way.
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).  smem 160 KB -> one CTA per SM.
+#pragma once
+#include "attention_sm100.cuh"
+
+namespace f5 {
+
+struct Attn2Smem {
+  static constexpr int kQ = 0;                        // 2 x (128 x 64 bf16)
+  static constexpr int kK = 2 * 16384;                // 2 stages
+  static constexpr int kV = kK + 2 * 16384;           // 2 stages
+  static constexpr int kP = kV + 2 * 16384;           // 2 groups x 32 KB
+  static constexpr int kBar = kP + 2 * 32768;
+  // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2]
+  static constexpr int kNumBars = 15;
+  static constexpr int kTotal = kBar + kNumBars * 8 + 16;
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+      "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1)
+attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Attn2Smem::kBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] per group
+  uint64_t* p_full = bars + 11;   // [2] per group
+  uint64_t* pv_done = bars + 13;  // [2] per group
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Attn2Smem::kNumBars);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int HD = p.H * 64;
+  int kv_len = p.kv_len ? p.kv_len[b] : p.N;
+  kv_len = min(max(kv_len, 1), p.N);
+  const int num_kv = (kv_len + 127) >> 7;
+  const bool g1_active = q0 + 128 < p.N;   // second query tile has at least one real row
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, g1_active ? 32768 : 16384);
+      tma_load_3d(smem + Attn2Smem::kQ, &tma_qkv, q_full, h * 64, q0, b);
+      if (g1_active) tma_load_3d(smem + Attn2Smem::kQ + 16384, &tma_qkv, q_full, h * 64, q0 + 128, b);
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], 16384);
+        tma_load_3d(smem + Attn2Smem::kK + s * 16384, &tma_qkv, &k_full[s], HD + h * 64, j * 128, b);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], 16384);
+        tma_load_3d(smem + Attn2Smem::kV + s * 16384, &tma_qkv, &v_full[s], 2 * HD + h * 64, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t sQ = smem_u32(smem + Attn2Smem::kQ);
+    const uint32_t sPbase = smem_u32(smem + Attn2Smem::kP);
+    const int ngroups = g1_active ? 2 : 1;
+    auto issue_S = [&](int g, int stage) {
+      const uint32_t sK = smem_u32(smem + Attn2Smem::kK + stage * 16384);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_f16_ss(tmem_base + g * 128, umma_desc_sw128(sQ + g * 16384 + k * 32, 16, 1024),
+                    umma_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k != 0);
+    };
+    auto issue_PV = [&](int g, int stage, bool acc) {
+      const uint32_t sV = smem_u32(smem + Attn2Smem::kV + stage * 16384);
+      const uint32_t sP = sPbase + g * 32768;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_f16_ss(tmem_base + 256 + g * 64,
+                    umma_desc_sw128(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(sV + k * 2048, 16384, 1024), idesc_o, (acc || k != 0) ? 1u : 0u);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (lane == 0) {
+      for (int g = 0; g < ngroups; ++g) {
+        issue_S(g, 0);
+        tc_commit(&s_full[g]);
+      }
+      tc_commit(&k_empty[0]);
+    }
+    __syncwarp();
+    for (int j = 0; j < num_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const bool more = j + 1 < num_kv;
+      mbar_wait(&v_full[s], ph);
+      if (more) mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
+      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(&p_full[g], j & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_PV(g, s, j > 0);
+          tc_commit(&pv_done[g]);
+          if (g == ngroups - 1) tc_commit(&v_empty[s]);
+          if (more) {
+            issue_S(g, s ^ 1);
+            tc_commit(&s_full[g]);
+            if (g == ngroups - 1) tc_commit(&k_empty[s ^ 1]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  } else {
+    // ===================== softmax groups =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;\n");
+    const int g = (warp - 4) >> 2;
+    if (g == 0 || g1_active) {
+      const int lg = warp & 3;
+      const int r = lg * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+      const uint32_t tmem_S = tmem_base + g * 128 + lane_addr;
+      const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_addr;
+      uint8_t* sP = smem + Attn2Smem::kP + g * 32768;
+      constexpr float kLog2e = 1.4426950408889634f;
+      float m_run = -INFINITY;   // true running max
+      float m_used = 0.f;        // max used for the exponentials / O / l (lags m_run by <= 8 in log2 units)
+      float l_run = 0.f;
+
+      for (int j = 0; j < num_kv; ++j) {
+        mbar_wait(&s_full[g], j & 1);
+        tc_fence_after();
+        uint32_t sv[128];
+        tmem_ld32(tmem_S + 0, sv);
+        tmem_ld32(tmem_S + 32, sv + 32);
+        tmem_ld32(tmem_S + 64, sv + 64);
+        tmem_ld32(tmem_S + 96, sv + 96);
+        tmem_wait_ld();
+        const int kv0 = j * 128;
+        if (kv0 + 128 > kv_len) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (kv0 + i >= kv_len) sv[i] = __float_as_uint(-INFINITY);
+        }
+        float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+        }
+        m_run = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // P_g smem and O_g TMEM are free once PV_g(j-1) has completed
+        if (j > 0) mbar_wait(&pv_done[g], (j - 1) & 1);
+        bool grow = (j == 0) || ((m_run - m_used) * kLog2e > 8.f);
+        if (__any_sync(0xffffffffu, grow)) {
+          if (j > 0) {
+            // rescale O_g and l to the new reference max (warp-uniform branch: tcgen05 ops are .aligned)
+            tc_fence_after();
+            const float sc = ex2_approx((m_used - m_run) * kLog2e);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(tmem_O + c * 32, ov);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * sc);
+              tmem_st32(tmem_O + c * 32, ov);
+            }
+            tmem_wait_st();
+            l_run *= sc;
+          }
+          m_used = m_run;
+        }
+        const float mb = m_used * kLog2e;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        uint8_t* prow = sP + r * 128;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {   // 16 chunks of 8 probabilities = 16 bytes
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), kLog2e, -mb));
+          l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
+          const int chunk = (c & 7) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + chunk * 16) =
+              make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                         pack_bf16x2(e[6], e[7]));
+        }
+        l_run += (l0 + l1) + (l2 + l3);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[g]);
+      }
+      // epilogue: O / l
+      mbar_wait(&pv_done[g], (num_kv - 1) & 1);
+      tc_fence_after();
+      const int n = q0 + g * 128 + r;
+      const float inv = 1.f / l_run;
+      __nv_bfloat16* o = p.out + ((size_t)b * p.N + (n < p.N ? n : 0)) * p.ldo + h * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(tmem_O + c * 32, ov);
+        tmem_wait_ld();
+        if (n < p.N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(o + c * 32 + i) = w;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace f5

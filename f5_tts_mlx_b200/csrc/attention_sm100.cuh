@@ -63,6 +63,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
   kv_len = min(max(kv_len, 1), p.N);
   const int num_kv = (kv_len + 127) >> 7;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
@@ -87,6 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -178,7 +180,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
           m_new = fmaxf(m_new, x);
         }
       }
-      const float alpha = exp2f((m_run - m_new) * kLog2e);
+      const float alpha = ex2_approx((m_run - m_new) * kLog2e);
       const float mb = m_new * kLog2e;
       float l_tile = 0.f;
       // pass 2: p = exp2(s*log2e - m*log2e), write bf16 P into the swizzled A-operand tile
@@ -191,8 +193,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float x0 = __uint_as_float(sv[i]), x1 = __uint_as_float(sv[i + 1]);
-          float p0 = exp2f(fmaf(x0, kLog2e, -mb));
-          float p1 = exp2f(fmaf(x1, kLog2e, -mb));
+          float p0 = ex2_approx(fmaf(x0, kLog2e, -mb));
+          float p1 = ex2_approx(fmaf(x1, kLog2e, -mb));
           if (partial) {
             if (kv0 + c * 32 + i >= kv_len) p0 = 0.f;
             if (kv0 + c * 32 + i + 1 >= kv_len) p1 = 0.f;

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(kMelWarps * 32)
 mel_kernel(const float* __restrict__ audio, int T, const float* __restrict__ window,
            const float* __restrict__ filt_t, int n_mels, int hop, float* __restrict__ out,
            int frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float2 Zs[kMelWarps][512];
   __shared__ float mags[kMelWarps][516];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,6 +81,8 @@ __device__ __forceinline__ float2 vocos_bin(const float* __restrict__ hrow, int 
 __global__ void __launch_bounds__(kMelWarps * 32)
 istft_frames_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ window,
                     float* __restrict__ frames_out, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float2 Zs[kMelWarps][512];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * kMelWarps + warp;
@@ -115,6 +119,8 @@ istft_frames_kernel(const float* __restrict__ h, int ldh, const float* __restric
 __global__ void __launch_bounds__(256)
 istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window, int n_frames,
                  int hop, int norm_sq, int trim, float* __restrict__ out, int out_len) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (j >= out_len) return;
@@ -150,8 +156,8 @@ int f5_mel_forward(const float* audio, int32_t batch, int32_t samples, const flo
              samples / hop);
   ProfScope ps(PROF_OTHER, 0.0, 4.0 * batch * (double)samples + 4.0 * batch * (double)frames * n_mels,
                (cudaStream_t)stream);
-  mel_kernel<<<dim3(cdiv(frames, kMelWarps), batch), kMelWarps * 32, 0, (cudaStream_t)stream>>>(
-      audio, samples, window, filters, n_mels, hop, out, frames);
+  F5_CHECK_CUDA(launch_kernel(mel_kernel, dim3(dim3(cdiv(frames, kMelWarps), batch)), dim3(kMelWarps * 32), 0, (cudaStream_t)stream, 
+      audio, samples, window, filters, n_mels, hop, out, frames));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -165,10 +171,10 @@ int f5_istft(const float* h, int64_t ldh, int32_t batch, int32_t frames, const f
   const int rows = batch * frames;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
-  istft_frames_kernel<<<cdiv(rows, kMelWarps), kMelWarps * 32, 0, st>>>(h, (int)ldh, window,
-                                                                       frames_scratch, rows);
-  istft_ola_kernel<<<dim3(cdiv(out_len, 256), batch), 256, 0, st>>>(frames_scratch, window, frames,
-                                                                   hop, norm_sq, trim, out, out_len);
+  F5_CHECK_CUDA(launch_kernel(istft_frames_kernel, dim3(cdiv(rows, kMelWarps)), dim3(kMelWarps * 32), 0, st, h, (int)ldh, window,
+                                                                       frames_scratch, rows));
+  F5_CHECK_CUDA(launch_kernel(istft_ola_kernel, dim3(dim3(cdiv(out_len, 256), batch)), dim3(256), 0, st, frames_scratch, window, frames,
+                                                                   hop, norm_sq, trim, out, out_len));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

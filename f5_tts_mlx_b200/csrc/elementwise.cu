@@ -16,8 +16,8 @@ static int launch_ln_any(const float* x, void* yo, int rows, int dim, int rows_p
   switch (dim) {
 #define F5_LN_CASE(DD)                                                                         \
   case DD:                                                                                     \
-    ln_mod_kernel<DD, OUT_F32><<<blocks, 256, 0, st>>>(x, yo, rows, rows_per_batch, scale,     \
-                                                       shift, mod_batch_stride, add_one);      \
+    F5_CHECK_CUDA(launch_kernel(ln_mod_kernel<DD, OUT_F32>, dim3(blocks), dim3(256), 0, st, x, yo, rows, rows_per_batch, scale,     \
+                                                       shift, mod_batch_stride, add_one));      \
     break;
     F5_LN_CASE(256) F5_LN_CASE(512) F5_LN_CASE(768) F5_LN_CASE(1024) F5_LN_CASE(1536) F5_LN_CASE(2048)
 #undef F5_LN_CASE
@@ -48,9 +48,9 @@ int launch_dwconv7_ln(const float* x, void* y, int B, int N, int C, const float*
   const int blocks = cdiv(B * N * 32, 256);
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C) {
-    case 256: dwconv7_ln_kernel<256><<<blocks, 256, 0, st>>>(x, yo, B, N, wt, wb, ln_w, ln_b); break;
-    case 512: dwconv7_ln_kernel<512><<<blocks, 256, 0, st>>>(x, yo, B, N, wt, wb, ln_w, ln_b); break;
-    case 1024: dwconv7_ln_kernel<1024><<<blocks, 256, 0, st>>>(x, yo, B, N, wt, wb, ln_w, ln_b); break;
+    case 256: F5_CHECK_CUDA(launch_kernel(dwconv7_ln_kernel<256>, dim3(blocks), dim3(256), 0, st, x, yo, B, N, wt, wb, ln_w, ln_b)); break;
+    case 512: F5_CHECK_CUDA(launch_kernel(dwconv7_ln_kernel<512>, dim3(blocks), dim3(256), 0, st, x, yo, B, N, wt, wb, ln_w, ln_b)); break;
+    case 1024: F5_CHECK_CUDA(launch_kernel(dwconv7_ln_kernel<1024>, dim3(blocks), dim3(256), 0, st, x, yo, B, N, wt, wb, ln_w, ln_b)); break;
     default: return set_error(F5_ERR_INVALID, "dwconv7_ln: unsupported channels %d", C);
   }
   F5_CHECK_CUDA(cudaGetLastError());
@@ -62,15 +62,15 @@ int launch_grn(const void* h, void* y, float* nx_scratch, const float* gamma, co
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   F5_REQUIRE(h && y && nx_scratch && gamma && beta, "grn: null pointer");
   F5_REQUIRE(C % 4 == 0, "grn: C %% 4");
-  F5_CHECK_CUDA(cudaMemsetAsync(nx_scratch, 0, sizeof(float) * (size_t)B * C, st));
-  const int rpb = 32;
-  grn_sumsq_kernel<<<dim3(cdiv(N, rpb), B), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h), nx_scratch, N, C, rpb);
-  grn_finalize_kernel<<<B, 256, 0, st>>>(nx_scratch, C);
+  const int nblk = cdiv(N, kGrnRowsPerBlock);
+  F5_CHECK_CUDA(launch_kernel(grn_sumsq_kernel, dim3(nblk, B), dim3(256), 0, st,
+                              reinterpret_cast<const __nv_bfloat16*>(h), nx_scratch, N, C, nblk));
+  F5_CHECK_CUDA(launch_kernel(grn_finalize_kernel, dim3(B), dim3(256), 0, st, nx_scratch, C, nblk));
   const long long total4 = (long long)B * N * C / 4;
-  grn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h), reinterpret_cast<__nv_bfloat16*>(y), nx_scratch,
-      gamma, beta, N, C, total4);
+  F5_CHECK_CUDA(launch_kernel(grn_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st,
+                              reinterpret_cast<const __nv_bfloat16*>(h),
+                              reinterpret_cast<__nv_bfloat16*>(y), (const float*)nx_scratch,
+                              (long long)(1 + nblk) * C, gamma, beta, N, C, total4));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -81,8 +81,8 @@ int launch_text_embed_gather(const int* text, int B, int nt, int N, int C, const
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   F5_REQUIRE(text && emb && pos_table && x, "text_embed_gather: null pointer");
   F5_REQUIRE(C % 4 == 0, "text_embed_gather: C %% 4");
-  text_embed_gather_kernel<<<dim3(N, Bout), 128, 0, st>>>(text, B, nt, N, C, emb, pos_table,
-                                                          max_pos, x, drop_from);
+  F5_CHECK_CUDA(launch_kernel(text_embed_gather_kernel, dim3(dim3(N, Bout)), dim3(128), 0, st, text, B, nt, N, C, emb, pos_table,
+                                                          max_pos, x, drop_from));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -92,8 +92,8 @@ int launch_time_mlp(const float* tvals, int T, int D, const float* w0, const flo
                     cudaStream_t st) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   F5_REQUIRE(tvals && w0 && b0 && w2 && b2 && silu_bf16, "time_mlp: null pointer");
-  time_mlp_kernel<<<T, 256, (256 + D) * sizeof(float), st>>>(
-      tvals, D, w0, b0, w2, b2, t_emb, reinterpret_cast<__nv_bfloat16*>(silu_bf16));
+  F5_CHECK_CUDA(launch_kernel(time_mlp_kernel, dim3(T, cdiv(D, kTimeMlpCols)), dim3(256), (256 + D) * sizeof(float), st, 
+      tvals, D, w0, b0, w2, b2, t_emb, reinterpret_cast<__nv_bfloat16*>(silu_bf16)));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -101,7 +101,7 @@ int launch_time_mlp(const float* tvals, int T, int D, const float* w0, const flo
 int launch_ode_update(const OdeUpdateParams& p, cudaStream_t st) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   const long long tot = (long long)p.rows * p.d;
-  cfg_ode_update_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p);
+  F5_CHECK_CUDA(launch_kernel(cfg_ode_update_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, p));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -110,8 +110,8 @@ int launch_cast_pad_bf16(const float* src, int d, void* dst, int ld, int rows,
                          long long copy_row_offset, cudaStream_t st) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   const long long tot = (long long)rows * ld;
-  cast_pad_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-      src, d, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, copy_row_offset);
+  F5_CHECK_CUDA(launch_kernel(cast_pad_bf16_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, 
+      src, d, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, copy_row_offset));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -120,8 +120,8 @@ int launch_concat_cond_text(const float* cond, int dc, int Bc, int N, const floa
                             void* dst, int ld, int rows, int drop_from_row, cudaStream_t st) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   const long long tot = (long long)rows * ld;
-  concat_cond_text_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-      cond, dc, Bc, N, text, dt, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, drop_from_row);
+  F5_CHECK_CUDA(launch_kernel(concat_cond_text_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, 
+      cond, dc, Bc, N, text, dt, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, drop_from_row));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256)
 ln_mod_kernel(const float* __restrict__ x, void* __restrict__ y, int rows,
               int rows_per_batch, const float* __restrict__ scale, const float* __restrict__ shift,
               long long mod_batch_stride, int add_one) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int IT = D / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(256)
 dwconv7_ln_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int N,
                   const float* __restrict__ wt, const float* __restrict__ wb,
                   const float* __restrict__ ln_w, const float* __restrict__ ln_b) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int IT = C / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,15 +129,23 @@ dwconv7_ln_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, in
 // ---------------------------------------------------------------------------------------------
 // GRN (convnext_v2.py:15-18): Gx[b,c] = ||x[b,:,c]||_2 over ALL N frames (padded ones included),
 // Nx = Gx / (mean_c Gx + 1e-6), y = gamma * (x * Nx) + beta + x.
-// Three tiny kernels: column sum of squares (atomics into [B, C]), per-utterance finalise, apply.
-// h: bf16 [B, N, C].
+// Three tiny kernels, DETERMINISTIC (no atomics: with fp32 atomics the summation order changes run
+// to run, and the 1-ulp noise is amplified to ~1e-3 by the bf16 roundings downstream, which broke
+// bitwise reproducibility of sample()): per-32-frame partial sums of squares -> fixed-order
+// reduction + per-utterance normalisation -> apply.
+// h: bf16 [B, N, C]; scratch: fp32 [B, 1 + ceil(N/32), C] (slot 0 = Nx, slots 1.. = partials).
 // ---------------------------------------------------------------------------------------------
+constexpr int kGrnRowsPerBlock = 32;
+
 __global__ void __launch_bounds__(256)
-grn_sumsq_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ sumsq, int N, int C,
-                 int rows_per_block) {
+grn_sumsq_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ scratch, int N, int C,
+                 int nblk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(N, r0 + rows_per_block);
+  const int r0 = blockIdx.x * kGrnRowsPerBlock;
+  const int r1 = min(N, r0 + kGrnRowsPerBlock);
+  float* part = scratch + ((size_t)b * (1 + nblk) + 1 + blockIdx.x) * C;
   for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int r = r0; r < r1; ++r) {
@@ -143,30 +155,41 @@ grn_sumsq_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ sumsq,
       const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
       a0 += f0.x * f0.x; a1 += f0.y * f0.y; a2 += f1.x * f1.x; a3 += f1.y * f1.y;
     }
-    float* o = sumsq + (size_t)b * C + c4;
-    atomicAdd(o, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2); atomicAdd(o + 3, a3);
+    *reinterpret_cast<float4*>(part + c4) = make_float4(a0, a1, a2, a3);
   }
 }
 
-// in place: sumsq[b, c] -> Nx[b, c]
-__global__ void __launch_bounds__(256) grn_finalize_kernel(float* __restrict__ sumsq, int C) {
+// slot 0 of the utterance's scratch <- Nx[c]
+__global__ void __launch_bounds__(256)
+grn_finalize_kernel(float* __restrict__ scratch, int C, int nblk) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8];
-  float* row = sumsq + (size_t)blockIdx.x * C;
+  float* base = scratch + (size_t)blockIdx.x * (1 + nblk) * C;
   float s = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s += sqrtf(row[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float q = 0.f;
+    for (int k = 0; k < nblk; ++k) q += base[(size_t)(1 + k) * C + c];
+    const float gx = sqrtf(q);
+    base[c] = gx;
+    s += gx;
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   float tot = 0.f;
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
   const float denom = tot / C + 1e-6f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) row[c] = sqrtf(row[c]) / denom;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) base[c] = base[c] / denom;
 }
 
 __global__ void __launch_bounds__(256)
 grn_apply_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ y,
-                 const float* __restrict__ nx, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, int N, int C, long long total4) {
+                 const float* __restrict__ nx, long long nx_batch_stride,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, int N, int C,
+                 long long total4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const long long e = i4 * 4;
@@ -175,7 +198,7 @@ grn_apply_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict_
   const uint2 u = *reinterpret_cast<const uint2*>(h + e);
   const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
   const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  const float4 n4 = *reinterpret_cast<const float4*>(nx + (size_t)b * C + c);
+  const float4 n4 = *reinterpret_cast<const float4*>(nx + (size_t)b * nx_batch_stride + c);
   const float4 g = *reinterpret_cast<const float4*>(gamma + c);
   const float4 bt = *reinterpret_cast<const float4*>(beta + c);
   const float a0 = g.x * (f0.x * n4.x) + bt.x + f0.x;
@@ -196,6 +219,8 @@ __global__ void __launch_bounds__(128)
 text_embed_gather_kernel(const int* __restrict__ text, int B, int nt, int N, int C,
                          const float* __restrict__ emb, const float* __restrict__ pos_table,
                          int max_pos, float* __restrict__ x, int drop_from) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x, bo = blockIdx.y;
   const int b = bo % B;
   int id = 0;
@@ -221,17 +246,22 @@ text_embed_gather_kernel(const int* __restrict__ text, int B, int nt, int N, int
 //   e = 1000 t exp(-i ln(1e4)/127), [sin e | cos e] (256) -> Linear(256->D) -> SiLU -> Linear(D->D)
 // Outputs t_emb fp32 [T, D] (optional) and silu(t_emb) as bf16 [T, D], the A operand of the
 // AdaLN modulation-table GEMM (dit.py:267,286 apply SiLU to t before their Linear).
-// One block per time value; one warp per output feature (coalesced weight rows).
+// Grid (T, D/64): every block recomputes the cheap first layer (256 x D MACs) for its time value and
+// then produces 64 features of the second layer; one warp per output feature, coalesced weight rows.
 // ---------------------------------------------------------------------------------------------
+constexpr int kTimeMlpCols = 64;
 __global__ void __launch_bounds__(256)
 time_mlp_kernel(const float* __restrict__ tvals, int D, const float* __restrict__ w0,
                 const float* __restrict__ b0, const float* __restrict__ w2,
                 const float* __restrict__ b2, float* __restrict__ t_emb,
                 __nv_bfloat16* __restrict__ silu_bf16) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* h0 = sm;         // 256
   float* h1 = sm + 256;   // D
   const int ti = blockIdx.x;
+  const int o0 = blockIdx.y * kTimeMlpCols;
   const float t = tvals[ti];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (threadIdx.x < 128) {
@@ -244,12 +274,13 @@ time_mlp_kernel(const float* __restrict__ tvals, int D, const float* __restrict_
   for (int o = warp; o < D; o += nw) {
     const float* wr = w0 + (size_t)o * 256;
     float s = 0.f;
+#pragma unroll
     for (int k = lane; k < 256; k += 32) s += wr[k] * h0[k];
     s = warp_sum(s);
     if (lane == 0) h1[o] = silu_f(s + b0[o]);
   }
   __syncthreads();
-  for (int o = warp; o < D; o += nw) {
+  for (int o = o0 + warp; o < min(D, o0 + kTimeMlpCols); o += nw) {
     const float* wr = w2 + (size_t)o * D;
     float s = 0.f;
     for (int k = lane; k < D; k += 32) s += wr[k] * h1[k];
@@ -272,6 +303,8 @@ time_mlp_kernel(const float* __restrict__ tvals, int D, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) cfg_ode_update_kernel(const OdeUpdateParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)p.rows * p.d) return;
   const int r = (int)(i / p.d), c = (int)(i - (long long)r * p.d);
@@ -302,6 +335,8 @@ __global__ void __launch_bounds__(256) cfg_ode_update_kernel(const OdeUpdatePara
 __global__ void __launch_bounds__(256)
 cast_pad_bf16_kernel(const float* __restrict__ src, int d, __nv_bfloat16* __restrict__ dst, int ld,
                      int rows, long long copy_row_offset) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * ld) return;
   const int r = (int)(i / ld), c = (int)(i - (long long)r * ld);
@@ -317,6 +352,8 @@ __global__ void __launch_bounds__(256)
 concat_cond_text_kernel(const float* __restrict__ cond, int dc, int Bc, int N,
                         const float* __restrict__ text, int dt, __nv_bfloat16* __restrict__ dst,
                         int ld, int rows, int drop_from_row) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * ld) return;
   const int r = (int)(i / ld), c = (int)(i - (long long)r * ld);

@@ -1,4 +1,6 @@
 // Host launcher + C-ABI entry for the tcgen05 GEMM (see gemm_sm100.cuh and include/f5_b200.h).
+#include <stdlib.h>
+
 #include "gemm_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "host_common.h"
@@ -21,7 +23,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  kern<<<grid, 192, S::kTotal, stream>>>(ta, tb, p);
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(192), S::kTotal, stream, ta, tb, p));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -68,7 +70,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  kern<<<2 * clusters, 256, S::kTotal, stream>>>(ta, tb, p, n_tiles, total_tiles);
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(256), S::kTotal, stream, ta, tb, p, n_tiles, total_tiles));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -119,6 +121,14 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
   if (a->gate) F5_REQUIRE(a->gate_ld % 4 == 0, "f5_gemm_bf16: gate_ld not multiple of 4");
 
   int variant = a->variant;
+  {
+    static int forced = -1;   // debugging aid: F5_GEMM_VARIANT=1|2 overrides the automatic choice
+    if (forced < 0) {
+      const char* v = getenv("F5_GEMM_VARIANT");
+      forced = v ? atoi(v) : 0;
+    }
+    if (forced == 1 || forced == 2) variant = forced;
+  }
   if (a->conv_grouped) variant = 1;            // grouped conv: 64-wide column blocks, single-CTA kernel
   if (variant == 0) {
     // measured on B200 (tests/gpu_checks/check_gemm2.py): the persistent CTA-pair kernel with 256-wide
@@ -145,6 +155,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
     p2.rope = reinterpret_cast<const float2*>(a->rope);
     p2.rope_cols = a->rope_cols; p2.q_scale = a->q_scale; p2.q_cols = a->q_cols;
     p2.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p2.ldo2 = (int)a->ldo2;
+    p2.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
     {
@@ -199,6 +210,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
   p.q_cols = a->q_cols;
   p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16);
   p.ldo2 = (int)a->ldo2;
+  p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows

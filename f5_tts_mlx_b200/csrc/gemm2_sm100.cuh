@@ -118,6 +118,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int num_kb = p.conv_taps * kb_per_tap;
   const int pair_tiles_per_batch = p.tiles_per_batch;   // in units of 256-row pair tiles
 
+  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 0);
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -139,6 +141,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 1);
+  pdl_wait();
+  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 2);
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -166,8 +171,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
           tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
           tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * 64, n0 + (int)rank * (BN / 2));
+          if (kcount == 0) ts_mark(p, blockIdx.x, 3);
         }
       }
+      ts_mark(p, blockIdx.x, 4);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -186,6 +193,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (lane == 0) {
+            if (kcount == 0) ts_mark(p, blockIdx.x, 5);
             const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
             const uint32_t sb = sa + S::kABytes;
 #pragma unroll
@@ -200,6 +208,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           __syncwarp();
         }
       }
+      if (lane == 0) ts_mark(p, blockIdx.x, 6);
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs) =====================
@@ -231,6 +240,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
+      if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
       const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -245,6 +255,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
     }
+    if (warp == 4 && lane == 0) ts_mark(p, blockIdx.x, 8);
   }
 
   tc_fence_before();
@@ -253,6 +264,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
+  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 9);
 }
 
 }  // namespace f5

@@ -33,7 +33,16 @@ struct GemmParams {
   int q_cols;
   __nv_bfloat16* out2;     // optional bf16 copy of the result
   int ldo2;
+  unsigned long long* ts;  // debug: per-CTA phase timestamps (globaltimer ns), 10 slots per CTA, or null
 };
+
+__device__ __forceinline__ void ts_mark(const GemmParams& p, int cta, int slot) {
+  if (p.ts != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.ts[(size_t)cta * 10 + slot] = t;
+  }
+}
 
 // acc: 32 fp32 accumulator columns [col0, col0+32) of output row `row` (utterance b_idx, frame pos)
 template <int ACT, bool OUT_BF16, bool ROPE>

@@ -68,7 +68,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int kb_per_tap = (p.k_per_tap + 63) >> 6;
   const int num_kb = p.conv_taps * kb_per_tap;
 
-  // ---- one-time setup ----
+  // ---- one-time setup (overlaps the predecessor kernel under PDL) ----
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) ts_mark(p, cta_lin, 0);
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -87,6 +90,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) ts_mark(p, cta_lin, 1);
+  pdl_wait();   // predecessor's outputs (our A operand / residual) are complete and visible
+  if (threadIdx.x == 0) ts_mark(p, cta_lin, 2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -104,7 +110,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
                     p.tiles_per_batch > 0 ? batch : 0);
         tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
+        if (kb == 0) ts_mark(p, cta_lin, 3);
       }
+      ts_mark(p, cta_lin, 4);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -115,6 +123,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
+        if (kb == 0) ts_mark(p, cta_lin, 5);
         const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
         const uint32_t sb = sa + S::kABytes;
 #pragma unroll
@@ -124,7 +133,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         tc_commit(&empty_bar[s]);                        // frees the smem slot when MMAs retire
-        if (kb == num_kb - 1) tc_commit(tmem_full_bar);  // accumulator complete
+        if (kb == num_kb - 1) {
+          tc_commit(tmem_full_bar);  // accumulator complete
+          ts_mark(p, cta_lin, 6);
+        }
       }
       __syncwarp();
     }
@@ -152,6 +164,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 7);
 
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -163,6 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       gemm_epilogue_chunk<ACT, OUT_BF16, ROPE>(acc, p, col0, row, pos, b_idx, row_ok, row_valid);
     }
     tc_fence_before();
+    if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 8);
   }
 
   __syncthreads();
@@ -170,6 +184,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
+  if (threadIdx.x == 0) ts_mark(p, cta_lin, 9);
 }
 
 }  // namespace f5

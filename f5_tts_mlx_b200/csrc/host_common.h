@@ -36,6 +36,24 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with the programmatic-dependent-launch attribute (see ptx.cuh); F5_PDL=0 disables it.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- launch accounting + optional per-kernel-family device timing (bench.py roofline) ----
 // Every launcher opens a ProfScope around its kernel launch.  The launch counter is always on;
 // when profiling is enabled (f5_prof_enable) a CUDA event pair brackets the launch on its stream

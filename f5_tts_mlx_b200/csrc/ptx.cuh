@@ -32,6 +32,18 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may START (barrier init, TMEM alloc, descriptor prefetch) while its predecessor in the
+// stream is still running; pdl_wait() blocks until the predecessor grid has fully completed and its
+// memory is visible.  Every kernel in this library calls pdl_launch_dependents() first thing and
+// pdl_wait() before its first global-memory access; both are no-ops for ordinary launches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -233,6 +245,14 @@ __device__ __forceinline__ float mish_f(float x) {
   return x * tanhf(sp);
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+// 2^x on the MUFU pipe, one instruction (exp2f() adds a denormal-range pre/post scale: FSETP + 2 FMUL
+// per call, which tripled the instruction count of the softmax inner loop); ex2(-inf) = 0.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

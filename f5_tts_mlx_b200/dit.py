@@ -66,7 +66,7 @@ class DitSession:
         self.text_a = z(R, Ct, dt=bf16)
         self.text_h = z(R, 2 * Ct, dt=bf16)
         self.text_g = z(R, 2 * Ct, dt=bf16)
-        self.grn_nx = z(BU, 2 * Ct)
+        self.grn_nx = z(BU, 1 + (frames + 31) // 32, 2 * Ct)
         self.ct_bf16 = z(R, ct_ld, dt=bf16)
         self.silu_t = z(n_times, D, dt=bf16)
         self.y_bf16 = z(R, 128, dt=bf16)

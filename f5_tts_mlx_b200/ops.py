@@ -54,6 +54,7 @@ def gemm(
     conv_grouped: bool = False,
     tile_n: int = 0,
     variant: int = 0,
+    debug_ts: torch.Tensor | None = None,
 ) -> torch.Tensor:
     _need_cuda(a, w, out, bias, resid, gate, row_len, rope)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -89,5 +90,7 @@ def gemm(
     g.rope_cols, g.q_scale, g.q_cols = rope_cols, q_scale, q_cols
     g.tile_n = tile_n
     g.variant = variant
+    if debug_ts is not None:
+        g.debug_ts = debug_ts.data_ptr()
     _lib.check(_lib.load().f5_gemm_bf16(C.byref(g), _stream()))
     return out

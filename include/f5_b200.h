@@ -95,6 +95,7 @@ typedef struct f5_gemm_args {
   int64_t ldo2;
   int32_t variant;        /* 0 auto | 1 single-CTA 128xBN tiles | 2 persistent CTA-pair 256xBN    */
   int32_t reserved;
+  void* debug_ts;         /* NULL, or uint64 [ctas, 10]: per-CTA phase timestamps (globaltimer ns)  */
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
@@ -118,7 +119,8 @@ int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
  * f5_dwconv7_ln  : depthwise Conv1d(k=7,pad=3)+bias then affine LayerNorm (convnext_v2.py:35-38,
  *                  48-49).  x fp32 [batch, frames, C]; w_tap_major fp32 [7, C]; y bf16.
  * f5_grn         : GRN over the frame axis (convnext_v2.py:15-18). h,y bf16 [batch, frames, C];
- *                  nx_scratch fp32 [batch, C].
+ *                  nx_scratch fp32 [batch, 1 + ceil(frames/32), C] (deterministic two-stage
+ *                  reduction: slot 0 receives Nx, the rest per-32-frame partial sums).
  * ------------------------------------------------------------------------------------------ */
 int f5_ln_modulate(const float* x, void* y_bf16, int32_t rows, int32_t dim, int32_t rows_per_batch,
                    const float* scale, const float* shift, int64_t mod_batch_stride,
@@ -203,7 +205,7 @@ typedef struct f5_dit_buffers {
   void* text_a;               /* bf16 [rows, text_dim] */
   void* text_h;               /* bf16 [rows, text_inner] */
   void* text_g;               /* bf16 [rows, text_inner] */
-  float* grn_nx;              /* fp32 [rows/frames, text_inner] */
+  float* grn_nx;              /* fp32 [rows/frames, 1 + ceil(frames/32), text_inner] (f5_grn scratch) */
   void* ct_bf16;              /* bf16 [rows, ct_ld] */
   void* silu_t;               /* bf16 [n_times, D] */
   void* y_bf16;               /* bf16 [rows, 128]: current ODE state, A operand of the x-projection */

@@ -156,7 +156,7 @@ def test_dwconv7_ln_and_grn():
     assert rel(y, ref.reshape(B * N, Cc)) < 4e-3
     Ci = 1024
     h = rnd(B, N, Ci).bfloat16(); gamma = rnd(Ci) * 0.5; beta = rnd(Ci) * 0.5
-    out = torch.empty_like(h); nx = torch.empty(B, Ci, device=dev)
+    out = torch.empty_like(h); nx = torch.empty(B, 1 + (N + 31) // 32, Ci, device=dev)
     _lib.check(lib.f5_grn(h.data_ptr(), out.data_ptr(), nx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, N, Ci, st))
     hf = h.float()
     Gx = hf.pow(2).sum(1, keepdim=True).sqrt()
