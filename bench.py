@@ -259,6 +259,9 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     f5.use_cuda_graph = False
     c0 = lib.f5_launch_count()
     lib.f5_prof_enable(1)
+    # keep the GPU busy while the host enqueues the ~5000 launches + event pairs of the step, so the
+    # event intervals measure device time (kernel + dependency gap), not host launch latency
+    torch.cuda._sleep(int(0.25 * 1.9e9))
     f5.sample(cond_d, text, N, y0=y0_d, **kw)
     torch.cuda.synchronize()
     prof = (C.c_double * 16)()

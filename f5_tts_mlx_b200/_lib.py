@@ -60,6 +60,7 @@ class GemmArgs(C.Structure):
         ("out2_bf16", C.c_void_p), ("ldo2", C.c_int64),
         ("variant", C.c_int32), ("reserved", C.c_int32),
         ("debug_ts", C.c_void_p),
+        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]
 
 
@@ -73,6 +74,7 @@ SYMBOLS: dict[str, tuple] = {
     "f5_prof_enable": (C.c_int, [C.c_int]),
     "f5_prof_summary": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "f5_debug_gemm_ts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "f5_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "f5_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

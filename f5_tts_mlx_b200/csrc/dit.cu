@@ -6,6 +6,7 @@
 //   * cond·Wc + text·Wt + b of InputEmbedding.proj    -> once per sample (dit.py:249)
 //   * TimestepEmbedding + all 23 AdaLN linears         -> one GEMM over all time points (dit.py:389,267,286)
 // and the two unbatched CFG passes (cfm.py:342-363) run as one forward over a doubled batch.
+#include <stdlib.h>
 #include <string.h>
 
 #include "host_common.h"
@@ -111,6 +112,11 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   const int R = BU * N;
   const int NM = w->depth * 6 * D + 2 * D;
   const float* mod = b->mod_table + (size_t)ti * NM;
+  // weight prefetch chain: worthwhile while a GEMM's weights are comparable to its activations
+  // (small batch); at large batch the activations evict them anyway and HBM is busy
+  static int pf_env = -1;
+  if (pf_env < 0) { const char* v = getenv("F5_PREFETCH"); pf_env = (v && v[0] == '0') ? 0 : 1; }
+  const bool prefetch = pf_env && R <= 16384;
 
   // ---- InputEmbedding (dit.py:249-251): x·Wx + hoist, then + ConvPositionEmbedding ----
   {
@@ -145,6 +151,8 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.bias = bw.qkv_b;
       g.rows_per_batch = N; g.num_batches = BU;
       g.rope = b->rope; g.rope_cols = 2 * D; g.q_scale = 0.125f; g.q_cols = D;
+      // weight prefetch chain (L2): while QKV runs, pull in out_w and ff1_w (contiguous in the pack)
+      if (prefetch) { g.prefetch = bw.out_w; g.prefetch_bytes = (int64_t)2 * D * D; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
     if (int e = f5_attention_fwd(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64, b->seq_len, st))
@@ -155,12 +163,14 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.rows_per_batch = N; g.num_batches = BU; g.row_len = b->seq_len;
       g.gate = m + 2 * D; g.gate_ld = 0;
       g.resid = b->x; g.ldr = D;
+      if (prefetch) { g.prefetch = bw.ff1_w; g.prefetch_bytes = (int64_t)2 * F * D; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
     if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + 4 * D, m + 3 * D, 0, 1, st)) return e;
     {
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.ff1_w, D, R, F, D, b->ff_bf16, F, true);
       g.bias = bw.ff1_b; g.act = F5_ACT_GELU_TANH;
+      if (prefetch) { g.prefetch = bw.ff2_w; g.prefetch_bytes = (int64_t)2 * D * F; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
     {
@@ -169,6 +179,9 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.rows_per_batch = N; g.num_batches = BU;
       g.gate = m + 5 * D; g.gate_ld = 0;
       g.resid = b->x; g.ldr = D;
+      if (prefetch && l + 1 < w->depth) {
+        g.prefetch = w->blocks[l + 1].qkv_w; g.prefetch_bytes = (int64_t)2 * 3 * D * D;
+      }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
   }

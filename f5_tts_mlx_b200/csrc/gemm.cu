@@ -95,9 +95,27 @@ static int dispatch_epi2(int act, bool out_bf16, bool rope, const CUtensorMap& t
 
 }  // namespace f5
 
-extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
+// Debug aid: give successive f5_gemm_bf16 calls consecutive slices of a timestamp buffer, so the
+// per-CTA phase timelines of every GEMM of a (graph-captured) step can be read back in situ.
+static char* g_ts_base = nullptr;
+static long long g_ts_stride = 0;
+static int g_ts_max = 0, g_ts_idx = 0;
+extern "C" int f5_debug_gemm_ts(void* base, int64_t stride_bytes, int32_t max_calls) {
+  g_ts_base = reinterpret_cast<char*>(base);
+  g_ts_stride = stride_bytes;
+  g_ts_max = max_calls;
+  g_ts_idx = 0;
+  return 0;
+}
+
+extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   using namespace f5;
   if (int e = device_check()) return e;
+  F5_REQUIRE(a_in != nullptr, "f5_gemm_bf16: null args");
+  f5_gemm_args a_copy = *a_in;
+  if (g_ts_base && g_ts_idx < g_ts_max && a_copy.debug_ts == nullptr)
+    a_copy.debug_ts = g_ts_base + (long long)(g_ts_idx++) * g_ts_stride;
+  const f5_gemm_args* a = &a_copy;
   F5_REQUIRE(a != nullptr, "f5_gemm_bf16: null args");
   F5_REQUIRE(a->a && a->w && a->out, "f5_gemm_bf16: null operand pointer");
   F5_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "f5_gemm_bf16: bad shape m=%d n=%d k=%d", a->m,
@@ -156,6 +174,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
     p2.rope_cols = a->rope_cols; p2.q_scale = a->q_scale; p2.q_cols = a->q_cols;
     p2.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16); p2.ldo2 = (int)a->ldo2;
     p2.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
+    p2.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p2.pf_bytes = a->prefetch_bytes;
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
     {
@@ -211,6 +230,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream_) {
   p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2_bf16);
   p.ldo2 = (int)a->ldo2;
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
+  p.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p.pf_bytes = a->prefetch_bytes;
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows

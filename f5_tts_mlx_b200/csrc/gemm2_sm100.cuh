@@ -91,7 +91,8 @@ struct Gemm2Smem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
-  static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;  // + align slack
+  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN])
+  static constexpr int kTotal = kColsOffset + 4 * BN * 4 + 1024;  // + align slack
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
@@ -137,6 +138,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
     tmem_relinquish_2sm();
   }
+  if (warp == 3) prefetch_slice_l2(p, blockIdx.x, gridDim.x, lane);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -238,19 +240,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       bool row_valid = true;
       if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
 
+      // operand staging for this tile (overlaps the MMAs still filling the accumulator)
+      float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * 2 * BN;
+      float* gate_s = bias_s + BN;
+      epi_stage_cols<BN>(p, n0, (warp - 4) * 32 + lane, bias_s, gate_s);
+      float2 cs[ROPE ? 32 : 1];
+      epi_load_rope<ROPE>(p, pos, cs);
+      float4 res0[8];
+      epi_load_resid(p, row, n0, row_ok, res0);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
       if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
-      const uint32_t tmem_acc = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_acc + c * 32, acc);
-        tmem_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) continue;
-        gemm_epilogue_chunk<ACT, OUT_BF16, ROPE>(acc, p, col0, row, pos, b_idx, row_ok, row_valid);
-      }
+      epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
+                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);

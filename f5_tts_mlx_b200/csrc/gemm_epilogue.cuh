@@ -34,7 +34,22 @@ struct GemmParams {
   __nv_bfloat16* out2;     // optional bf16 copy of the result
   int ldo2;
   unsigned long long* ts;  // debug: per-CTA phase timestamps (globaltimer ns), 10 slots per CTA, or null
+  const char* pf_ptr;      // weights of a LATER GEMM to pull into L2 while this one runs, or null
+  long long pf_bytes;
 };
+
+// Each CTA touches its 1/num_ctas slice of [pf_ptr, pf_ptr + pf_bytes) with L2 prefetches (one warp,
+// 128 B per lane per iteration).  At batch 1 the 0.67 GB of weights stream from HBM once per DiT
+// evaluation and every GEMM used to start cold (3-stage TMA ring vs ~1 us HBM latency per k-block);
+// HBM has >20x the bandwidth this needs, so the next GEMMs' weights are fetched ahead of time.
+__device__ __forceinline__ void prefetch_slice_l2(const GemmParams& p, int cta, int num_ctas, int lane) {
+  if (p.pf_ptr == nullptr) return;
+  const long long per = (((p.pf_bytes + num_ctas - 1) / num_ctas) + 127) & ~127LL;
+  const long long lo = (long long)cta * per;
+  const long long hi = lo + per < p.pf_bytes ? lo + per : p.pf_bytes;
+  for (long long o = lo + (long long)lane * 128; o < hi; o += 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf_ptr + o));
+}
 
 __device__ __forceinline__ void ts_mark(const GemmParams& p, int cta, int slot) {
   if (p.ts != nullptr) {
@@ -44,42 +59,104 @@ __device__ __forceinline__ void ts_mark(const GemmParams& p, int cta, int slot) 
   }
 }
 
-// acc: 32 fp32 accumulator columns [col0, col0+32) of output row `row` (utterance b_idx, frame pos)
-template <int ACT, bool OUT_BF16, bool ROPE>
-__device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[32], const GemmParams& p,
-                                                    int col0, int row, int pos, int b_idx,
-                                                    bool row_ok, bool row_valid) {
+// ---------------------------------------------------------------------------------------------
+// Epilogue, organised for memory-level parallelism.  In-situ timelines of the B=1 step showed the
+// first version (load bias -> use -> load gate -> use -> load residual -> use, per 32-column chunk,
+// libm tanhf) spending ~10 us per GEMM in the epilogue against a 6 us main loop.  Now:
+//   * bias and gate of the tile's columns are staged in shared memory once (epi_stage_cols);
+//   * the RoPE cos/sin of the thread's row (32 pairs = one head) are loaded into registers BEFORE the
+//     accumulator is awaited (epi_load_rope), as is the residual of the first chunk; the residual of
+//     chunk c+1 is requested before chunk c is processed (double buffer);
+//   * activations use the MUFU approximations (tanh.approx / ex2.approx / lg2.approx).
+// One thread owns one output row; a chunk is 32 consecutive accumulator columns.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * fmaf(k1 * x * x, x, x);
+  return 0.5f * x * (1.f + tanh_approx(u));
+}
+__device__ __forceinline__ float mish_fast(float x) {
+  // x * tanh(softplus(x)), softplus = log(1 + e^x) (= x beyond 15)
+  const float sp = x > 15.f ? x : __logf(1.f + __expf(x));
+  return x * tanh_approx(sp);
+}
+
+// stage bias[n0..n0+BN) and gate[n0..n0+BN) (gate only when it is shared by all utterances,
+// gate_ld == 0) into shared memory; called by the 128 epilogue threads, `et` = 0..127
+template <int BN>
+__device__ __forceinline__ void epi_stage_cols(const GemmParams& p, int n0, int et, float* bias_s,
+                                               float* gate_s) {
+#pragma unroll
+  for (int i = et; i < BN; i += 128) {
+    const int col = n0 + i;
+    bias_s[i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.f;
+    gate_s[i] = (p.gate != nullptr && p.gate_ld == 0 && col < p.N) ? p.gate[col] : 1.f;
+  }
+}
+
+template <bool ROPE>
+__device__ __forceinline__ void epi_load_rope(const GemmParams& p, int pos, float2 (&cs)[ROPE ? 32 : 1]) {
+  if (ROPE) {
+    const float4* rp = reinterpret_cast<const float4*>(p.rope + (size_t)pos * 32);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 v = rp[j];
+      cs[2 * j] = make_float2(v.x, v.y);
+      cs[2 * j + 1] = make_float2(v.z, v.w);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_load_resid(const GemmParams& p, int row, int col0, bool row_ok,
+                                               float4 (&r)[8]) {
+  if (p.resid != nullptr && row_ok && col0 < p.N) {
+    const float4* rr = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = (col0 + 4 * j < p.N) ? rr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// HALF: which 32-column half of a 64-column head this chunk is (static RoPE register indexing)
+template <int ACT, bool OUT_BF16, bool ROPE, int HALF>
+__device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float4 (&res)[8],
+                                          const float* bias_s, const float* gate_s,
+                                          const float2 (&cs)[ROPE ? 32 : 1], const GemmParams& p,
+                                          int col0, int row, int b_idx, bool row_ok, bool row_valid) {
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (col0 + j < p.N) {
-        float4 bb = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-      }
-    }
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+    v[j] = __uint_as_float(acc[j]) + bb.x;
+    v[j + 1] = __uint_as_float(acc[j + 1]) + bb.y;
+    v[j + 2] = __uint_as_float(acc[j + 2]) + bb.z;
+    v[j + 3] = __uint_as_float(acc[j + 3]) + bb.w;
   }
   if (ACT == ACT_GELU_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
   } else if (ACT == ACT_GELU_ERF) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
   } else if (ACT == ACT_MISH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = mish_f(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = mish_fast(v[j]);
   }
   if (ROPE) {
     if (col0 < p.rope_cols) {
-      const float2* rp = p.rope + (size_t)pos * 32 + ((col0 & 63) >> 1);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float2 cs = rp[j];
-        float a = v[2 * j], b = v[2 * j + 1];
-        v[2 * j] = a * cs.x - b * cs.y;
-        v[2 * j + 1] = b * cs.x + a * cs.y;
+        const float2 c = cs[HALF * 16 + j];
+        const float a = v[2 * j], b = v[2 * j + 1];
+        v[2 * j] = a * c.x - b * c.y;
+        v[2 * j + 1] = b * c.x + a * c.y;
       }
     }
     if (col0 < p.q_cols) {
@@ -92,62 +169,77 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const uint32_t (&acc)[32], c
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
   if (p.gate != nullptr) {
-    const float* g = p.gate + (size_t)b_idx * p.gate_ld + col0;
+    if (p.gate_ld == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (col0 + j < p.N) {
-        float4 gg = *reinterpret_cast<const float4*>(g + j);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 gg = *reinterpret_cast<const float4*>(gate_s + j);
         v[j] *= gg.x; v[j + 1] *= gg.y; v[j + 2] *= gg.z; v[j + 3] *= gg.w;
       }
+    } else {   // per-utterance gates (not used by sample(): all utterances share the time value)
+      const float* g = p.gate + (size_t)b_idx * p.gate_ld + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] *= g[j];
     }
   }
-  if (row_ok) {
-    if (p.resid != nullptr) {
-      const float* rr = p.resid + (size_t)row * p.ldr + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (col0 + j < p.N) {
-          float4 x = *reinterpret_cast<const float4*>(rr + j);
-          v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-        }
-      }
+  for (int j = 0; j < 8; ++j) {
+    v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+  }
+  if (!row_ok) return;
+  if (p.out2 != nullptr) {
+    __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (col0 + j < p.N)
+        *reinterpret_cast<uint4*>(o2 + j) =
+            make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                       pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
     }
-    if (p.out2 != nullptr) {
-      __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+  }
+  if (OUT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (col0 + j < p.N) {
-          uint4 w;
-          w.x = pack_bf16x2(v[j], v[j + 1]);
-          w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(o2 + j) = w;
-        }
-      }
+    for (int j = 0; j < 32; j += 8) {
+      if (col0 + j < p.N)
+        *reinterpret_cast<uint4*>(o + j) =
+            make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                       pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
     }
-    if (OUT_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (col0 + j < p.N) {
-          uint4 w;
-          w.x = pack_bf16x2(v[j], v[j + 1]);
-          w.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          w.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          w.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(o + j) = w;
-        }
-      }
-    } else {
-      float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (col0 + j < p.N) {
-          *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      }
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
+  }
+}
+
+// Drains one accumulator tile of BN columns: TMEM base `tmem_acc` (lane group already applied).
+template <int BN, int ACT, bool OUT_BF16, bool ROPE>
+__device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* bias_s,
+                                               const float* gate_s, const float2 (&cs)[ROPE ? 32 : 1],
+                                               float4 (&res0)[8], const GemmParams& p, int n0, int row,
+                                               int b_idx, bool row_ok, bool row_valid) {
+  float4 res1[8];
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 64; ++cc) {
+    const int colA = n0 + cc * 64, colB = colA + 32;
+    uint32_t acc[32];
+    // chunk A (first half of the head): request chunk B's residual, then drain A
+    epi_load_resid(p, row, colB, row_ok, res1);
+    tmem_ld32(tmem_acc + cc * 64, acc);
+    tmem_wait_ld();
+    if (colA < p.N)
+      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
+                                        b_idx, row_ok, row_valid);
+    // chunk B: request the next pair's first residual, then drain B
+    if (cc + 1 < BN / 64) epi_load_resid(p, row, colA + 64, row_ok, res0);
+    tmem_ld32(tmem_acc + cc * 64 + 32, acc);
+    tmem_wait_ld();
+    if (colB < p.N)
+      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res1, bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs, p,
+                                        colB, row, b_idx, row_ok, row_valid);
   }
 }
 

@@ -34,11 +34,12 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;  // + align slack
+  static constexpr int kColsOffset = (kBarOffset + (2 * kStages + 1) * 8 + 16 + 15) & ~15;   // bias_s[BN], gate_s[BN] (float4 reads)
+  static constexpr int kTotal = kColsOffset + 2 * BN * 4 + 1024;  // + align slack
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using S = GemmSmem<BN, kStages>;
@@ -86,6 +87,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tmem_alloc(tmem_ptr_smem, BN);
     tmem_relinquish();
   }
+  if (warp == 2) prefetch_slice_l2(p, cta_lin, gridDim.x * gridDim.y, lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -162,18 +164,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     bool row_valid = true;
     if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
 
+    // operand staging, overlapped with the main loop
+    float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset);
+    float* gate_s = bias_s + BN;
+    epi_stage_cols<BN>(p, n0, (warp - 2) * 32 + lane, bias_s, gate_s);
+    float2 cs[ROPE ? 32 : 1];
+    epi_load_rope<ROPE>(p, pos, cs);
+    float4 res0[8];
+    epi_load_resid(p, row, n0, row_ok, res0);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // bias_s / gate_s visible to the 4 epilogue warps
+
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 7);
-
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + c * 32, acc);
-      tmem_wait_ld();
-      const int col0 = n0 + c * 32;
-      if (col0 >= p.N) continue;  // uniform per CTA
-      gemm_epilogue_chunk<ACT, OUT_BF16, ROPE>(acc, p, col0, row, pos, b_idx, row_ok, row_valid);
+    if (BN >= 64) {
+      epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s, gate_s, cs,
+                                              res0, p, n0, row, b_idx, row_ok, row_valid);
     }
     tc_fence_before();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 8);

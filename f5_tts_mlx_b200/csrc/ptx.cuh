@@ -254,6 +254,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for a PAIR of inputs on the FMA/ALU pipes only (no MUFU): round-to-nearest split x = n + f,
+// |f| <= 0.5, degree-3 minimax polynomial for 2^f (max rel. error 7.5e-5, far below the bf16
+// rounding of the probabilities it feeds), 2^n applied by adding n to the exponent field.  Used for
+// a fraction of the softmax exponentials so that the MUFU pipe (16 ex2/clk/SM) stops being the
+// bound of the attention kernel.  Inputs must be <= ~0 and are clamped at -126.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 r = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(make_float2(0.055171646f, 0.055171646f), f, make_float2(0.24261113f, 0.24261113f));
+  p = __ffma2_rn(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = __ffma2_rn(p, f, make_float2(0.99992806f, 0.99992806f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

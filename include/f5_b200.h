@@ -96,9 +96,14 @@ typedef struct f5_gemm_args {
   int32_t variant;        /* 0 auto | 1 single-CTA 128xBN tiles | 2 persistent CTA-pair 256xBN    */
   int32_t reserved;
   void* debug_ts;         /* NULL, or uint64 [ctas, 10]: per-CTA phase timestamps (globaltimer ns)  */
+  const void* prefetch;   /* NULL, or device memory (weights of a later GEMM) to pull into L2       */
+  int64_t prefetch_bytes;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
+/* debug aid: the next `max_calls` f5_gemm_bf16 calls without their own debug_ts write their per-CTA
+ * timestamps to base + i * stride_bytes (i = call index); pass NULL to stop. */
+int f5_debug_gemm_ts(void* base, int64_t stride_bytes, int32_t max_calls);
 
 /* ------------------------------------------------------------------------------------------ *
  * Flash-attention forward (non-causal, key-padding mask, head_dim 64) — replaces

@@ -1,7 +1,11 @@
 export PYTHONPATH=.
-python tests/gpu_checks/check_determinism.py 2>&1 | tail -8
-python tests/gpu_checks/check_cfg_equiv.py 2>&1 | tail -8
-python tests/gpu_checks/check_attention.py 2>&1 | tail -6
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench2.json 2> gpurun_out/bench2.err; tail -c 1800 gpurun_out/bench2.json; tail -3 gpurun_out/bench2.err
-F5_PDL=0 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('PDL off: ms/step', d['ms_per_step'], 'value', d['value'])"
+python tests/gpu_checks/run.py check_gemm check_gemm2 2>&1 | grep -E "OK|FAIL|time M1874|ALL" | cut -c 1-330
+python tests/gpu_checks/check_insitu.py 2>&1 | tail -14
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench4.json 2> gpurun_out/bench4.err; tail -2 gpurun_out/bench4.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench4.json').read().strip().splitlines()[-1])
+print('ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'])
+print(json.dumps(d['roofline'])[:900])
+PY
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
