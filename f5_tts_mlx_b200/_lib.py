@@ -86,6 +86,7 @@ SYMBOLS: dict[str, tuple] = {
     "f5_dit_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_dit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "f5_ode_eval_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32]),
+    "f5_duration_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_mel_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_int32, C.c_void_p]),
     "f5_istft": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

@@ -77,12 +77,12 @@ int launch_grn(const void* h, void* y, float* nx_scratch, const float* gamma, co
 
 int launch_text_embed_gather(const int* text, int B, int nt, int N, int C, const float* emb,
                              const float* pos_table, int max_pos, float* x, int Bout,
-                             int drop_from, cudaStream_t st) {
+                             int drop_from, cudaStream_t st, int mask_padding) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   F5_REQUIRE(text && emb && pos_table && x, "text_embed_gather: null pointer");
   F5_REQUIRE(C % 4 == 0, "text_embed_gather: C %% 4");
   F5_CHECK_CUDA(launch_kernel(text_embed_gather_kernel, dim3(dim3(N, Bout)), dim3(128), 0, st, text, B, nt, N, C, emb, pos_table,
-                                                          max_pos, x, drop_from));
+                                                          max_pos, x, drop_from, mask_padding));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -117,12 +117,26 @@ int launch_cast_pad_bf16(const float* src, int d, void* dst, int ld, int rows,
 }
 
 int launch_concat_cond_text(const float* cond, int dc, int Bc, int N, const float* text, int dt,
-                            void* dst, int ld, int rows, int drop_from_row, cudaStream_t st) {
+                            void* dst, int ld, int rows, int drop_from_row, cudaStream_t st,
+                            const int* cond_len) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   const long long tot = (long long)rows * ld;
   F5_CHECK_CUDA(launch_kernel(concat_cond_text_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, 
-      cond, dc, Bc, N, text, dt, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, drop_from_row));
+      cond, dc, Bc, N, text, dt, reinterpret_cast<__nv_bfloat16*>(dst), ld, rows, drop_from_row, cond_len));
   F5_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_duration_head(const float* x, int B, int N, int D, const int* len, const float* norm_w,
+                         const float* pred_w, float* out, cudaStream_t st) {
+  ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
+  F5_REQUIRE(x && len && norm_w && pred_w && out, "duration_head: null pointer");
+  switch (D) {
+    case 256: F5_CHECK_CUDA(launch_kernel(duration_head_kernel<256>, dim3(B), dim3(256), 0, st, x, N, len, norm_w, pred_w, out)); break;
+    case 512: F5_CHECK_CUDA(launch_kernel(duration_head_kernel<512>, dim3(B), dim3(256), 0, st, x, N, len, norm_w, pred_w, out)); break;
+    case 1024: F5_CHECK_CUDA(launch_kernel(duration_head_kernel<1024>, dim3(B), dim3(256), 0, st, x, N, len, norm_w, pred_w, out)); break;
+    default: return set_error(F5_ERR_INVALID, "duration_head: unsupported dim %d", D);
+  }
   return 0;
 }
 

@@ -218,14 +218,14 @@ grn_apply_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict_
 __global__ void __launch_bounds__(128)
 text_embed_gather_kernel(const int* __restrict__ text, int B, int nt, int N, int C,
                          const float* __restrict__ emb, const float* __restrict__ pos_table,
-                         int max_pos, float* __restrict__ x, int drop_from) {
+                         int max_pos, float* __restrict__ x, int drop_from, int mask_padding) {
   pdl_launch_dependents();
   pdl_wait();
   const int n = blockIdx.x, bo = blockIdx.y;
   const int b = bo % B;
   int id = 0;
   if (n < nt) id = text[(size_t)b * nt + n] + 1;
-  const bool masked = (id == 0);
+  const bool masked = mask_padding && (id == 0);   // DurationTransformer: mask_padding=False (duration.py:118-120)
   if (bo >= drop_from) id = 0;
   const int p = n < max_pos ? n : max_pos - 1;
   const float4* er = reinterpret_cast<const float4*>(emb + (size_t)id * C);
@@ -351,7 +351,7 @@ cast_pad_bf16_kernel(const float* __restrict__ src, int d, __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 concat_cond_text_kernel(const float* __restrict__ cond, int dc, int Bc, int N,
                         const float* __restrict__ text, int dt, __nv_bfloat16* __restrict__ dst,
-                        int ld, int rows, int drop_from_row) {
+                        int ld, int rows, int drop_from_row, const int* __restrict__ cond_len) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -361,12 +361,69 @@ concat_cond_text_kernel(const float* __restrict__ cond, int dc, int Bc, int N,
   if (c < dc) {
     if (r < drop_from_row) {
       const int b = (r / N) % Bc, n = r % N;
-      v = cond[((size_t)b * N + n) * dc + c];
+      // DurationPredictor zeroes the mel beyond each utterance's length (duration.py:241-243)
+      if (cond_len == nullptr || n < cond_len[b]) v = cond[((size_t)b * N + n) * dc + c];
     }
   } else if (c < dc + dt) {
     v = text[(size_t)r * dt + (c - dc)];
   }
   dst[i] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DurationPredictor head (duration.py:129,187-189,246-247): nn.RMSNorm(dim) (eps 1e-5, weight),
+// masked mean over the frames n < len[b], Linear(dim -> 1, no bias), Softplus -> seconds.
+// One block per utterance, deterministic (fixed row partition per warp, fixed-order reduction).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+duration_head_kernel(const float* __restrict__ x, int N, const int* __restrict__ len,
+                     const float* __restrict__ norm_w, const float* __restrict__ pred_w,
+                     float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int IT = D / 128;
+  __shared__ float4 part[8][D / 4];
+  __shared__ float red[8];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = min(max(len[b], 0), N);
+  float4 acc[IT];
+#pragma unroll
+  for (int i = 0; i < IT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int n = warp; n < L; n += 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + ((size_t)b * N + n) * D);
+    float4 v[IT];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      v[i] = xr[i * 32 + lane];
+      q += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+    const float r = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      acc[i].x += v[i].x * r; acc[i].y += v[i].y * r; acc[i].z += v[i].z * r; acc[i].w += v[i].w * r;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < IT; ++i) part[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  float s = 0.f;
+  const float inv_len = 1.f / (float)max(L, 1);
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float m = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) m += reinterpret_cast<const float*>(part[w])[c];
+    s += m * inv_len * norm_w[c] * pred_w[c];
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[b] = t > 20.f ? t : log1pf(expf(t));   // Softplus
+  }
 }
 
 }  // namespace f5

@@ -159,7 +159,15 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   if (variant == 2) {
     int bn2 = a->tile_n;
     if (bn2 == 0) bn2 = (a->n % 256 == 0 || a->n >= 1024) ? 256 : 128;
-    F5_REQUIRE(bn2 == 128 || bn2 == 256, "f5_gemm_bf16: CTA-pair tile_n must be 128 or 256");
+    // wide outputs on few row tiles (QKV at batch 1: 8 x 12 tiles of 256 columns on 74 SM pairs = two
+    // rounds, the second 30 % full): 192-column tiles give 8 x 16 smaller tiles
+    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0) {
+      const int t256 = cdiv(a->m, 256) * cdiv(a->n, 256), t192 = cdiv(a->m, 256) * cdiv(a->n, 192);
+      const int pairs = 74;
+      const double c256 = (double)cdiv(t256, pairs) * 256, c192 = (double)cdiv(t192, pairs) * 192;
+      if (c192 < 0.85 * c256) bn2 = 192;   // only when it removes a mostly-empty round
+    }
+    F5_REQUIRE(bn2 == 128 || bn2 == 192 || bn2 == 256, "f5_gemm_bf16: CTA-pair tile_n must be 128, 192 or 256");
     GemmParams p2;
     p2.M = a->m; p2.N = a->n; p2.K = a->k;
     p2.rows_per_batch = rpb;
@@ -194,9 +202,11 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     const int m_tiles = batched ? nb * cdiv(rpb, 256) : cdiv(a->m, 256);
     cudaStream_t stream2 = reinterpret_cast<cudaStream_t>(stream_);
     const bool rope2 = a->rope != nullptr;
+    if (bn2 == 192)
+      return dispatch_epi2<192, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
     if (bn2 == 256)
-      return dispatch_epi2<256, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
-    return dispatch_epi2<128, 8>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+      return dispatch_epi2<256, 5>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+    return dispatch_epi2<128, 7>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
   }
 
   int bn = a->tile_n;
@@ -253,6 +263,10 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   dim3 grid(cdiv(a->n, bn), batched ? nb * cdiv(rpb, 128) : cdiv(a->m, 128), 1);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const bool rope = a->rope != nullptr;
+  // grids that fit in one wave leave one CTA per SM anyway: spend the whole smem on a 6-stage ring
+  // (192 KB in flight per SM instead of 96 KB) to cover the L2/HBM latency of the operand stream
+  if (bn == 128 && (long long)grid.x * grid.y <= 148)
+    return dispatch_epi<128, 6>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
   if (bn == 128) return dispatch_epi<128, 3>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
   return dispatch_epi<64, 4>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
 }

@@ -92,7 +92,8 @@ struct Gemm2Smem {
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN])
-  static constexpr int kTotal = kColsOffset + 4 * BN * 4 + 1024;  // + align slack
+  static constexpr int kStageOutOffset = (kColsOffset + 4 * BN * 4 + 127) & ~127;   // 2 x 16 KB store staging
+  static constexpr int kTotal = kStageOutOffset + 32768 + 1024;  // + align slack
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
@@ -135,7 +136,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc_2sm(tmem_ptr_smem, 2 * BN);
+    tmem_alloc_2sm(tmem_ptr_smem, BN > 128 ? 512 : 256);   // 2 accumulator stages, power of two
     tmem_relinquish_2sm();
   }
   if (warp == 3) prefetch_slice_l2(p, blockIdx.x, gridDim.x, lane);
@@ -224,6 +225,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       const uint32_t aph = (acount >> 1) & 1;
       int row, pos, b_idx;
       bool row_ok;
+      const int b_idx_tile = pair_tiles_per_batch > 0 ? m_tile / pair_tiles_per_batch : 0;
       if (pair_tiles_per_batch > 0) {
         b_idx = m_tile / pair_tiles_per_batch;
         pos = (m_tile % pair_tiles_per_batch) * 256 + r_in_tile;
@@ -253,8 +255,20 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
       if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
+      EpiStage stg;
+      stg.buf = smem + S::kStageOutOffset;
+      stg.et = (warp - 4) * 32 + lane;
+      stg.r = lg * 32 + lane;
+      if (pair_tiles_per_batch > 0) {
+        const int m0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
+        stg.row0 = (long long)b_idx_tile * p.rows_per_batch + m0;
+        stg.rows_valid = min(128, p.rows_per_batch - m0);
+      } else {
+        stg.row0 = (long long)m_tile * 256 + (int)rank * 128;
+        stg.rows_valid = min(128, p.M - (int)stg.row0);
+      }
       epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
-                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid);
+                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
@@ -266,7 +280,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, 2 * BN);
+    tmem_dealloc_2sm(tmem_base, BN > 128 ? 512 : 256);
   }
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 9);
 }

@@ -124,12 +124,69 @@ __device__ __forceinline__ void epi_load_resid(const GemmParams& p, int row, int
   }
 }
 
+// Coalesced stores: a thread owns a ROW, so its 16-byte stores land in 32 different rows per warp
+// instruction (half-sector writes 4 KB apart — measured 5-6 us per 128x128 fp32 tile in situ).
+// Instead every chunk (128 rows x 32 columns) is written to a swizzled shared-memory buffer and
+// then stored cooperatively, 8 (fp32) or 4 (bf16) consecutive lanes covering one row segment, i.e.
+// full 128 B / 64 B runs.  Two buffers alternate, one named barrier (128 epilogue threads) per chunk.
+struct EpiStage {
+  uint8_t* buf;            // 2 x 16 KB, or nullptr: direct per-thread stores
+  int et;                  // epilogue thread 0..127
+  int r;                   // this thread's row inside the tile
+  long long row0;          // global row of tile row 0
+  int rows_valid;          // rows of the tile that exist
+};
+
+template <bool OUT_BF16>
+__device__ __forceinline__ void epi_store_staged(const float (&v)[32], const EpiStage& st, int par,
+                                                 const GemmParams& p, int col0) {
+  uint8_t* buf = st.buf + par * 16384;
+  if (OUT_BF16) {
+    uint8_t* mine = buf + st.r * 64;
+    const int sw = (st.r >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(mine + ((j ^ sw) * 16)) =
+          make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const int q = st.et & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = i * 32 + (st.et >> 2);
+      if (row < st.rows_valid && col0 + q * 8 < p.N) {
+        const uint4 w = *reinterpret_cast<const uint4*>(buf + row * 64 + ((q ^ ((row >> 1) & 3)) * 16));
+        *reinterpret_cast<uint4*>(out + (size_t)(st.row0 + row) * p.ldo + col0 + q * 8) = w;
+      }
+    }
+  } else {
+    uint8_t* mine = buf + st.r * 128;
+    const int sw = st.r & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(mine + ((j ^ sw) * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* out = reinterpret_cast<float*>(p.out);
+    const int q = st.et & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 16 + (st.et >> 3);
+      if (row < st.rows_valid && col0 + q * 4 < p.N) {
+        const float4 w = *reinterpret_cast<const float4*>(buf + row * 128 + ((q ^ (row & 7)) * 16));
+        *reinterpret_cast<float4*>(out + (size_t)(st.row0 + row) * p.ldo + col0 + q * 4) = w;
+      }
+    }
+  }
+}
+
 // HALF: which 32-column half of a 64-column head this chunk is (static RoPE register indexing)
 template <int ACT, bool OUT_BF16, bool ROPE, int HALF>
 __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float4 (&res)[8],
                                           const float* bias_s, const float* gate_s,
                                           const float2 (&cs)[ROPE ? 32 : 1], const GemmParams& p,
-                                          int col0, int row, int b_idx, bool row_ok, bool row_valid) {
+                                          int col0, int row, int b_idx, bool row_ok, bool row_valid,
+                                          const EpiStage& st) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -186,6 +243,20 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
   for (int j = 0; j < 8; ++j) {
     v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
   }
+  if (st.buf != nullptr) {
+    if (p.out2 != nullptr && row_ok) {
+      __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (col0 + j < p.N)
+          *reinterpret_cast<uint4*>(o2 + j) =
+              make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                         pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+      }
+    }
+    epi_store_staged<OUT_BF16>(v, st, HALF, p, col0);   // all 128 threads take part (barrier inside)
+    return;
+  }
   if (!row_ok) return;
   if (p.out2 != nullptr) {
     __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
@@ -220,7 +291,8 @@ template <int BN, int ACT, bool OUT_BF16, bool ROPE>
 __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* bias_s,
                                                const float* gate_s, const float2 (&cs)[ROPE ? 32 : 1],
                                                float4 (&res0)[8], const GemmParams& p, int n0, int row,
-                                               int b_idx, bool row_ok, bool row_valid) {
+                                               int b_idx, bool row_ok, bool row_valid,
+                                               const EpiStage& st) {
   float4 res1[8];
 #pragma unroll 1
   for (int cc = 0; cc < BN / 64; ++cc) {
@@ -230,16 +302,16 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
     epi_load_resid(p, row, colB, row_ok, res1);
     tmem_ld32(tmem_acc + cc * 64, acc);
     tmem_wait_ld();
-    if (colA < p.N)
+    if (colA < p.N)   // uniform per CTA
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
-                                        b_idx, row_ok, row_valid);
+                                        b_idx, row_ok, row_valid, st);
     // chunk B: request the next pair's first residual, then drain B
     if (cc + 1 < BN / 64) epi_load_resid(p, row, colA + 64, row_ok, res0);
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res1, bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs, p,
-                                        colB, row, b_idx, row_ok, row_valid);
+                                        colB, row, b_idx, row_ok, row_valid, st);
   }
 }
 

@@ -177,9 +177,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 7);
-    if (BN >= 64) {
+    {
+      // all MMAs have retired (tmem_full), so the operand ring is idle: its first 32 KB stage the stores
+      EpiStage stg;
+      stg.buf = smem;
+      stg.et = (warp - 2) * 32 + lane;
+      stg.r = r_in_tile;
+      stg.row0 = row0;
+      stg.rows_valid = p.tiles_per_batch > 0 ? min(128, p.rows_per_batch - m_in_batch0) : min(128, p.M - row0);
       epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s, gate_s, cs,
-                                              res0, p, n0, row, b_idx, row_ok, row_valid);
+                                              res0, p, n0, row, b_idx, row_ok, row_valid, stg);
     }
     tc_fence_before();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 8);

@@ -150,12 +150,13 @@ int f5_prof_summary(double* out, int kinds) {
 }
 // sizeof() of every struct of the ABI, so a binding can verify its own layout at load time
 int f5_struct_sizes(int32_t* out, int32_t n) {
-  const int32_t v[8] = {(int32_t)sizeof(f5_gemm_args),          (int32_t)sizeof(f5_convnext_weights),
-                        (int32_t)sizeof(f5_dit_block_weights),  (int32_t)sizeof(f5_dit_weights),
-                        (int32_t)sizeof(f5_dit_buffers),        (int32_t)sizeof(f5_vocos_block_weights),
-                        (int32_t)sizeof(f5_vocos_weights),      (int32_t)sizeof(f5_vocos_buffers)};
-  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
-  return 8;
+  const int32_t v[10] = {(int32_t)sizeof(f5_gemm_args),          (int32_t)sizeof(f5_convnext_weights),
+                         (int32_t)sizeof(f5_dit_block_weights),  (int32_t)sizeof(f5_dit_weights),
+                         (int32_t)sizeof(f5_dit_buffers),        (int32_t)sizeof(f5_vocos_block_weights),
+                         (int32_t)sizeof(f5_vocos_weights),      (int32_t)sizeof(f5_vocos_buffers),
+                         (int32_t)sizeof(f5_duration_weights),   (int32_t)sizeof(f5_duration_buffers)};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  return 10;
 }
 const char* f5_last_error(void) { return f5::g_err; }
 int f5_abi_version(void) { return 1000; }

@@ -27,7 +27,7 @@ int launch_grn(const void* h, void* y, float* nx_scratch, const float* gamma, co
                int B, int N, int C, cudaStream_t st);
 int launch_text_embed_gather(const int* text, int B, int nt, int N, int C, const float* emb,
                              const float* pos_table, int max_pos, float* x, int Bout,
-                             int drop_from, cudaStream_t st);
+                             int drop_from, cudaStream_t st, int mask_padding = 1);
 int launch_time_mlp(const float* tvals, int T, int D, const float* w0, const float* b0,
                     const float* w2, const float* b2, float* t_emb, void* silu_bf16,
                     cudaStream_t st);
@@ -35,5 +35,8 @@ int launch_ode_update(const OdeUpdateParams& p, cudaStream_t st);
 int launch_cast_pad_bf16(const float* src, int d, void* dst, int ld, int rows,
                          long long copy_row_offset, cudaStream_t st);
 int launch_concat_cond_text(const float* cond, int dc, int Bc, int N, const float* text, int dt,
-                            void* dst, int ld, int rows, int drop_from_row, cudaStream_t st);
+                            void* dst, int ld, int rows, int drop_from_row, cudaStream_t st,
+                            const int* cond_len = nullptr);
+int launch_duration_head(const float* x, int B, int N, int D, const int* len, const float* norm_w,
+                         const float* pred_w, float* out, cudaStream_t st);
 }  // namespace f5

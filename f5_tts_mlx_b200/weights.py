@@ -119,6 +119,44 @@ def random_dit_weights(cfg: DiTConfig, seed: int = 1234, adaln_gain: float = 4.0
     return W
 
 
+def random_duration_weights(dim: int = 512, depth: int = 8, ff_mult: int = 2, text_dim: int = 512, conv_layers: int = 2,
+                            text_num_embeds: int = 2545, mel_dim: int = 100, seed: int = 777) -> Weights:
+    """Seeded random-init DurationPredictor weights with the MLX parameter names of duration_v2
+    (cfm.py:428-442): `transformer.…`, `to_pred.layers.0.weight`."""
+    rng = np.random.default_rng(seed)
+    D, F, Ct = dim, dim * ff_mult, text_dim
+    W: Weights = {}
+
+    def lin(name, out_f, in_f, bias=True):
+        W[name + ".weight"] = _uniform(rng, (out_f, in_f), in_f)
+        if bias:
+            W[name + ".bias"] = _uniform(rng, (out_f,), in_f)
+
+    T = "transformer."
+    W[T + "text_embed.text_embed.weight"] = _normal(rng, (text_num_embeds + 1, Ct), math.sqrt(1.0 / Ct))
+    for i in range(conv_layers):
+        p = T + f"text_embed.text_blocks.layers.{i}."
+        W[p + "dwconv.weight"] = _uniform(rng, (Ct, 7, 1), 7); W[p + "dwconv.bias"] = _uniform(rng, (Ct,), 7)
+        W[p + "norm.weight"] = _normal(rng, (Ct,), 0.1, 1.0); W[p + "norm.bias"] = _normal(rng, (Ct,), 0.1)
+        lin(p + "pwconv1", 2 * Ct, Ct)
+        W[p + "grn.gamma"] = _normal(rng, (1, 1, 2 * Ct), 0.5); W[p + "grn.beta"] = _normal(rng, (1, 1, 2 * Ct), 0.5)
+        lin(p + "pwconv2", Ct, 2 * Ct)
+    lin(T + "input_embed.proj", D, mel_dim + Ct)
+    for j in (0, 2):
+        p = T + f"input_embed.conv_pos_embed.conv1d.layers.{j}."
+        W[p + "weight"] = _uniform(rng, (D, 31, D // 16), 31 * (D // 16)); W[p + "bias"] = _uniform(rng, (D,), 31 * (D // 16))
+    for i in range(depth):
+        p = T + f"transformer_blocks.{i}."
+        for n in "qkv":
+            lin(p + f"attn.to_{n}", D, D)
+        lin(p + "attn.to_out.layers.0", D, D)
+        lin(p + "ff.ff.layers.0.layers.0", F, D)
+        lin(p + "ff.ff.layers.2", D, F)
+    W[T + "norm_out.weight"] = _normal(rng, (D,), 0.1, 1.0)
+    W["to_pred.layers.0.weight"] = _uniform(rng, (1, D), D, gain=8.0)
+    return W
+
+
 def random_vocos_weights(vc: VocosConfig = VocosConfig(), seed: int = 4321) -> Weights:
     rng = np.random.default_rng(seed)
     W: Weights = {}

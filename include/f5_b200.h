@@ -45,7 +45,8 @@ long long f5_launch_count(void);
  * 2 LayerNorm+modulate, 3 everything else. */
 /* sizeof() of the ABI structs in declaration order: f5_gemm_args, f5_convnext_weights,
  * f5_dit_block_weights, f5_dit_weights, f5_dit_buffers, f5_vocos_block_weights, f5_vocos_weights,
- * f5_vocos_buffers — lets a binding check its layout at load time.  Returns the count (8). */
+ * f5_vocos_buffers, f5_duration_weights, f5_duration_buffers — lets a binding check its layout at
+ * load time.  Returns the count (10). */
 int f5_struct_sizes(int32_t* out, int32_t n);
 int f5_prof_enable(int on);
 int f5_prof_summary(double* out, int kinds);
@@ -240,6 +241,39 @@ int f5_ode_eval_times(const float* h_t_grid, int32_t steps, int32_t method, floa
 int f5_ode_sample(const f5_dit_weights* w, const f5_dit_buffers* b, const float* h_t_grid,
                   int32_t steps, int32_t method, float cfg_strength, float* y, float* trajectory,
                   float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * DurationPredictor (duration.py:97-253, inference branch; call site cfm.py:253-262,307-308): runs
+ * once per sample() when duration=None.  mel fp32 [batch, frames, mel_dim] (frames >= text columns;
+ * rows beyond lens[b] are treated as zero, duration.py:241-243) + text ids -> seconds fp32 [batch].
+ * Reuses f5_convnext_weights / f5_dit_block_weights.  zeros: fp32 [dim] of zeros (the shift/scale
+ * of the non-affine LayerNorms).  in_w: bf16 [dim, ct_ld] = proj.weight over [mel | text], padded.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct f5_duration_weights {
+  int32_t dim, depth, heads, ff_inner, mel_dim, text_dim, text_inner, conv_layers;
+  int32_t text_rows, text_max_pos, ct_ld, reserved;
+  const float* text_emb; const float* text_pos;
+  const f5_convnext_weights* text_blocks;       /* HOST array [conv_layers] */
+  const void* in_w; const float* in_b;
+  const void* conv_w[2]; const float* conv_b[2];
+  const f5_dit_block_weights* blocks;           /* HOST array [depth] */
+  const float* zeros;
+  const float* norm_w;                          /* RMSNorm weight [dim] */
+  const float* pred_w;                          /* to_pred Linear(dim -> 1) weight [dim] */
+} f5_duration_weights;
+
+typedef struct f5_duration_buffers {
+  int32_t batch, frames, text_len_max, reserved;
+  const int32_t* text;        /* int32 [batch, text_len_max], pad -1 */
+  const int32_t* lens;        /* int32 [batch] valid frames */
+  const float* inp;           /* fp32 [batch, frames, mel_dim] */
+  const float* rope;          /* fp32 [frames, 32, 2] */
+  float* text_x; void* text_a; void* text_h; void* text_g; float* grn_nx; void* ct_bf16;
+  float* x; float* h; void* a_bf16; void* c_bf16; void* qkv_bf16; void* ff_bf16;
+  float* out;                 /* fp32 [batch] seconds */
+} f5_duration_buffers;
+
+int f5_duration_forward(const f5_duration_weights* w, const f5_duration_buffers* b, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Log-mel front-end — replaces log_mel_spectrogram / MelSpec (audio.py:162-230): zero-padded

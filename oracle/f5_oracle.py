@@ -260,8 +260,8 @@ def timestep_embedding(time: Tensor, W: Weights) -> Tensor:
 
 
 def text_embedding(text: Tensor, seq_len: int, drop_text: bool, W: Weights, cfg: DiTConfig,
-                   prec: Precision = FP32) -> Tensor:
-    """dit.py:196-229."""
+                   prec: Precision = FP32, prefix: str = "transformer.", mask_padding: bool = True) -> Tensor:
+    """dit.py:196-229 (mask_padding=False is how DurationTransformer builds it, duration.py:118-120)."""
     batch, text_len = text.shape
     text = text + 1                                                     # :200
     text = text[:, :seq_len]                                            # :203
@@ -269,22 +269,24 @@ def text_embedding(text: Tensor, seq_len: int, drop_text: bool, W: Weights, cfg:
     text_mask = (text == 0)[..., None]                                  # :207 (before the drop)
     if drop_text:
         text = torch.zeros_like(text)                                   # :210
-    x = W["transformer.text_embed.text_embed.weight"][text.long()]      # :211
+    x = W[prefix + "text_embed.text_embed.weight"][text.long()]          # :211
     if cfg.conv_layers > 0:
         max_pos = 4096                                                  # :190
         table = precompute_freqs_cis(cfg.text_dim, max_pos)
         pos_idx = get_pos_embed_indices(torch.zeros(batch, dtype=torch.int32), seq_len, max_pos)
         x = x + table[pos_idx.long()]                                   # :216-218
-        x = torch.where(text_mask, torch.zeros_like(x), x)              # :222
+        if mask_padding:
+            x = torch.where(text_mask, torch.zeros_like(x), x)          # :222
         for i in range(cfg.conv_layers):
-            x = convnext_v2_block(x, W, f"transformer.text_embed.text_blocks.layers.{i}.", prec)
-            x = torch.where(text_mask, torch.zeros_like(x), x)          # :223-225
+            x = convnext_v2_block(x, W, prefix + f"text_embed.text_blocks.layers.{i}.", prec)
+            if mask_padding:
+                x = torch.where(text_mask, torch.zeros_like(x), x)      # :223-225 (else :227)
     return x
 
 
-def conv_position_embedding(x: Tensor, W: Weights, prec: Precision = FP32) -> Tensor:
+def conv_position_embedding(x: Tensor, W: Weights, prec: Precision = FP32, prefix: str = "transformer.") -> Tensor:
     """dit.py:29-50 with mask=None (dit.py:251): Conv1d(k31,g16) Mish Conv1d Mish."""
-    p = "transformer.input_embed.conv_pos_embed.conv1d.layers."
+    p = prefix + "input_embed.conv_pos_embed.conv1d.layers."
     h = F.mish(conv1d_nlc(x, W[p + "0.weight"], W[p + "0.bias"], padding=15, groups=16, prec=prec))
     return F.mish(conv1d_nlc(h, W[p + "2.weight"], W[p + "2.bias"], padding=15, groups=16, prec=prec))
 
@@ -366,6 +368,66 @@ def dit_forward(x: Tensor, cond: Tensor, text: Tensor, time: Tensor, drop_audio_
     scale, shift = emb.chunk(2, dim=1)                                     # dit.py:287 (scale FIRST)
     x = F.layer_norm(x, (cfg.dim,), eps=1e-6) * (1 + scale[:, None]) + shift[:, None]
     return linear(x, W["transformer.proj_out.weight"], W["transformer.proj_out.bias"], prec)
+
+
+# ---------------------------------------------------------------------------------------------
+# duration.py — DurationPredictor (SURVEY §8f "next" row 1): runs once before the ODE loop when
+# `duration=None` (cfm.py:253-262, 307-308).
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class DurationConfig:
+    dim: int = 512
+    depth: int = 8
+    heads: int = 8
+    dim_head: int = 64
+    ff_mult: int = 2
+    mel_dim: int = 100
+    text_num_embeds: int = 2545
+    text_dim: int = 512
+    conv_layers: int = 2
+
+    def as_dit(self) -> "DiTConfig":
+        return DiTConfig(dim=self.dim, depth=self.depth, heads=self.heads, dim_head=self.dim_head, ff_mult=self.ff_mult,
+                         mel_dim=self.mel_dim, text_num_embeds=self.text_num_embeds, text_dim=self.text_dim,
+                         conv_layers=self.conv_layers)
+
+
+def duration_transformer(x: Tensor, text: Tensor, W: Weights, cfg: DurationConfig, prec: Precision = FP32) -> Tensor:
+    """duration.py:133-158.  Note: DurationPredictor calls it WITHOUT a mask (duration.py:245), so the
+    attention is unmasked; TextEmbedding is built with mask_padding=False."""
+    P = "duration.transformer."
+    b, n, _ = x.shape
+    text_embed = text_embedding(text, n, False, W, cfg.as_dit(), prec, prefix=P, mask_padding=False)
+    h = linear(torch.cat((x, text_embed), dim=-1), W[P + "input_embed.proj.weight"], W[P + "input_embed.proj.bias"], prec)
+    h = conv_position_embedding(h, W, prec, prefix=P) + h                       # duration.py:55-57
+    rope = rotary_freqs(n, cfg.dim_head)
+    for i in range(cfg.depth):                                                   # duration.py:81-94
+        p = P + f"transformer_blocks.{i}."
+        norm = F.layer_norm(h, (cfg.dim,), eps=1e-6)
+        h = h + attention(norm, None, rope, W, p + "attn.", cfg.heads, prec)
+        norm = F.layer_norm(h, (cfg.dim,), eps=1e-6)
+        f = linear(norm, W[p + "ff.ff.layers.0.layers.0.weight"], W[p + "ff.ff.layers.0.layers.0.bias"], prec)
+        f = F.gelu(f, approximate="tanh")
+        h = h + linear(f, W[p + "ff.ff.layers.2.weight"], W[p + "ff.ff.layers.2.bias"], prec)
+    # nn.RMSNorm(dim): x * rsqrt(mean(x^2) + 1e-5) * weight
+    return h * torch.rsqrt(h.pow(2).mean(dim=-1, keepdim=True) + 1e-5) * W[P + "norm_out.weight"]
+
+
+def duration_predictor(inp: Tensor, text: Tensor, W: Weights, cfg: DurationConfig, lens: Optional[Tensor] = None,
+                       prec: Precision = FP32) -> Tensor:
+    """duration.py:198-253 (inference branch): mel (b, n, 100) -> seconds (b,)."""
+    batch, seq_len = inp.shape[:2]
+    if seq_len < text.shape[1]:                                                  # :218-220
+        seq_len = text.shape[1]
+        inp = F.pad(inp, (0, 0, 0, seq_len - inp.shape[1]))
+    if lens is None:
+        lens = torch.full((batch,), seq_len)                                     # :224-225
+    mask = lens_to_mask(lens, length=seq_len)                                    # :231
+    inp = torch.where(mask[..., None], inp, torch.zeros_like(inp))               # :241-243
+    x = duration_transformer(inp, text, W, cfg, prec)                            # :245 (no mask passed)
+    x = torch.where(mask[..., None], x, torch.zeros_like(x))                     # maybe_masked_mean utils.py:82-90
+    x = x.sum(dim=1) / mask.sum(dim=1).clamp(min=1)[:, None]
+    return F.softplus(linear(x, W["duration.to_pred.layers.0.weight"], None, prec))[..., 0]   # :187-189
 
 
 # ---------------------------------------------------------------------------------------------

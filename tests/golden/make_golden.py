@@ -75,3 +75,16 @@ np.savez_compressed(os.path.join(HERE, "vocos_small.npz"), mel=mel.numpy(), wave
                     weight_seed=4321)
 for f in sorted(os.listdir(HERE)):
     print(f, os.path.getsize(os.path.join(HERE, f)))
+
+# (f) DurationPredictor
+from f5_tts_mlx_b200.weights import random_duration_weights  # noqa: E402
+dW = random_duration_weights(seed=777)
+dWo = {"duration." + k: v for k, v in dW.items()}
+gd = torch.Generator().manual_seed(21)
+mel = (torch.randn(2, 90, 100, generator=gd) * 2.24 - 1.27)
+text = torch.randint(0, 2545, (2, 30), generator=gd, dtype=torch.int32); text[1, 18:] = -1
+lens = torch.tensor([90, 61])
+sec = O.duration_predictor(mel, text, dWo, O.DurationConfig(), lens=lens)
+np.savez_compressed(os.path.join(HERE, "duration_small.npz"), mel=mel.numpy(), text=text.numpy(), lens=lens.numpy(),
+                    seconds=sec.numpy(), weight_seed=777)
+print("duration", sec)

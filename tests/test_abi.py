@@ -10,6 +10,7 @@ import torch
 
 from f5_tts_mlx_b200 import _lib
 from f5_tts_mlx_b200.dit import DitBuffersC
+from f5_tts_mlx_b200.duration import DurationBuffersC, DurationWeightsC
 from f5_tts_mlx_b200.vocos import VocosBlockWeightsC, VocosBuffersC, VocosWeightsC
 from f5_tts_mlx_b200.weights import ConvNextWeightsC, DitBlockWeightsC, DitWeightsC
 
@@ -35,10 +36,10 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_struct_layouts_match_ctypes():
     lib = _lib.load()
-    out = (C.c_int32 * 8)()
-    assert lib.f5_struct_sizes(out, 8) == 8
+    out = (C.c_int32 * 10)()
+    assert lib.f5_struct_sizes(out, 10) == 10
     mirrors = [_lib.GemmArgs, ConvNextWeightsC, DitBlockWeightsC, DitWeightsC, DitBuffersC, VocosBlockWeightsC,
-               VocosWeightsC, VocosBuffersC]
+               VocosWeightsC, VocosBuffersC, DurationWeightsC, DurationBuffersC]
     for got, m in zip(list(out), mirrors):
         assert got == C.sizeof(m), f"{m.__name__}: C sizeof {got} != ctypes {C.sizeof(m)}"
 

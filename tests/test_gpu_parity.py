@@ -257,3 +257,44 @@ def test_end_to_end_raw_wave_to_waveform(gate):
     ref, _ = O.sample(audio[None], text, N, W, ocfg_of(cfg), vocoder=lambda m: O.vocos_decode(m, vw), **kw)
     assert wave.ndim == 1 and wave.shape == ref.shape == ((N - 1) * 256 + 1024,)
     assert rel(wave.cpu(), ref) < 3e-2
+
+
+# ---------------- DurationPredictor ----------------
+def test_duration_predictor_vs_oracle_and_golden(golden_dir):
+    from f5_tts_mlx_b200.duration import DurationPredictor, DurationTransformer
+    from f5_tts_mlx_b200.weights import random_duration_weights
+    z = np.load(os.path.join(golden_dir, "duration_small.npz"))
+    dW = random_duration_weights(seed=int(z["weight_seed"]))
+    dWo = {"duration." + k: v for k, v in dW.items()}
+    pred = DurationPredictor(DurationTransformer(dim=512, depth=8, heads=8, text_dim=512, ff_mult=2, conv_layers=2,
+                                                 text_num_embeds=2545), device=dev).load_weights(dW)
+    mel, text, lens = torch.from_numpy(z["mel"]), torch.from_numpy(z["text"]), torch.from_numpy(z["lens"])
+    got = pred(mel.to(dev), text, lens=lens).cpu()
+    assert rel(got, torch.from_numpy(z["seconds"])) < 2e-2
+    # text longer than the mel (the mel is padded to the text length, duration.py:220-222), batch 1, no lens
+    g = torch.Generator().manual_seed(8)
+    mel1 = torch.randn(1, 40, 100, generator=g); text1 = torch.randint(0, 2545, (1, 70), generator=g, dtype=torch.int32)
+    ref = O.duration_predictor(mel1, text1, dWo, O.DurationConfig())
+    ref16 = O.duration_predictor(mel1, text1, dWo, O.DurationConfig(), prec=O.Precision(True))
+    got1 = pred(mel1.to(dev), text1).cpu()
+    assert abs(got1.item() - ref.item()) < max(3 * abs(ref16.item() - ref.item()), 2e-2 * abs(ref.item()))
+
+
+def test_sample_with_duration_predictor(gate):
+    """duration=None routes through predict_duration (cfm.py:253-262, integer frame rate 93)."""
+    from f5_tts_mlx_b200 import F5TTS
+    from f5_tts_mlx_b200.duration import DurationPredictor, DurationTransformer
+    from f5_tts_mlx_b200.weights import random_duration_weights
+    cfg, W, model = gate
+    dW = random_duration_weights(seed=5)
+    pred = DurationPredictor(DurationTransformer(dim=512, depth=8, heads=8, text_dim=512, ff_mult=2, conv_layers=2,
+                                                 text_num_embeds=2545), device=dev).load_weights(dW)
+    g = torch.Generator().manual_seed(9)
+    cond = (torch.randn(1, 60, 100, generator=g) * 2.24 - 1.27)
+    text = torch.randint(0, 2545, (1, 25), generator=g, dtype=torch.int32)
+    secs = O.duration_predictor(cond, text, {"duration." + k: v for k, v in dW.items()}, O.DurationConfig()).item()
+    expect = max(60 + 1, int(secs * 93 / 1.0))
+    out, _ = F5TTS(model, duration_predictor=pred).sample(cond.to(dev), text, None, steps=2, method="euler", seed=1)
+    assert abs(out.shape[1] - expect) <= 1 and torch.isfinite(out).all()
+    with pytest.raises(ValueError):
+        F5TTS(model).sample(cond.to(dev), text, None, steps=2, method="euler")

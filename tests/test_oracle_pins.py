@@ -215,3 +215,22 @@ def test_vocos_golden(golden_dir):
     assert w1.shape == (11 * 256 + 1024,) and rel(w1, torch.from_numpy(z["wave_window"])) < 5e-5
     w2 = O.vocos_decode(mel, vw, O.VocosConfig(istft_norm="window_sq", istft_trim=True))
     assert w2.shape == (11 * 256,) and rel(w2, torch.from_numpy(z["wave_window_sq_trim"])) < 5e-5
+
+
+# ---------------- DurationPredictor restatement ----------------
+def test_duration_predictor_golden_and_structure(golden_dir):
+    from f5_tts_mlx_b200.weights import random_duration_weights
+    z = np.load(os.path.join(golden_dir, "duration_small.npz"))
+    W = {"duration." + k: v for k, v in random_duration_weights(seed=int(z["weight_seed"])).items()}
+    mel, text, lens = torch.from_numpy(z["mel"]), torch.from_numpy(z["text"]), torch.from_numpy(z["lens"])
+    sec = O.duration_predictor(mel, text, W, O.DurationConfig(), lens=lens)
+    assert sec.shape == (2,) and (sec > 0).all()                       # Softplus output
+    assert rel(sec, torch.from_numpy(z["seconds"])) < 2e-5
+    # frames beyond lens[b] are zeroed on input but still attended to (no mask is passed, duration.py:245)
+    mel2 = mel.clone(); mel2[1, 61:] = 123.0
+    assert torch.allclose(O.duration_predictor(mel2, text, W, O.DurationConfig(), lens=lens), sec, atol=1e-6)
+    # RMSNorm as used by norm_out: x * rsqrt(mean(x^2) + 1e-5) * w
+    x = torch.randn(3, 7, 512)
+    ref = torch.nn.functional.rms_norm(x, (512,), W["duration.transformer.norm_out.weight"], eps=1e-5)
+    got = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * W["duration.transformer.norm_out.weight"]
+    assert torch.allclose(got, ref, atol=1e-5)
