@@ -315,4 +315,32 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
   }
 }
 
+// Variant for grids that fit in one wave (one CTA per SM, registers to spare): the residual of the
+// WHOLE tile is requested before the accumulator is awaited, so no residual latency is exposed in
+// the drain loop (the double-buffered variant above still exposes most of an L2 round trip per
+// chunk: its per-chunk work is much shorter than the latency it tries to cover).
+template <int BN, int ACT, bool OUT_BF16, bool ROPE>
+__device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, const float* bias_s,
+                                                         const float* gate_s,
+                                                         const float2 (&cs)[ROPE ? 32 : 1],
+                                                         float4 (&res)[BN / 32][8], const GemmParams& p,
+                                                         int n0, int row, int b_idx, bool row_ok,
+                                                         bool row_valid, const EpiStage& st) {
+#pragma unroll
+  for (int cc = 0; cc < BN / 64; ++cc) {
+    const int colA = n0 + cc * 64, colB = colA + 32;
+    uint32_t acc[32];
+    tmem_ld32(tmem_acc + cc * 64, acc);
+    tmem_wait_ld();
+    if (colA < p.N)
+      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
+                                        b_idx, row_ok, row_valid, st);
+    tmem_ld32(tmem_acc + cc * 64 + 32, acc);
+    tmem_wait_ld();
+    if (colB < p.N)
+      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res[2 * cc + 1], bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs,
+                                        p, colB, row, b_idx, row_ok, row_valid, st);
+  }
+}
+
 }  // namespace f5

@@ -39,7 +39,7 @@ struct GemmSmem {
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, (kStages > 4) ? 1 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using S = GemmSmem<BN, kStages>;
@@ -170,8 +170,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     epi_stage_cols<BN>(p, n0, (warp - 2) * 32 + lane, bias_s, gate_s);
     float2 cs[ROPE ? 32 : 1];
     epi_load_rope<ROPE>(p, pos, cs);
-    float4 res0[8];
-    epi_load_resid(p, row, n0, row_ok, res0);
+    constexpr bool kPreloadAll = (kStages > 4);   // single-wave variant: one CTA per SM
+    float4 res_all[kPreloadAll ? BN / 32 : 1][8];
+    if (kPreloadAll) {
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) epi_load_resid(p, row, n0 + c * 32, row_ok, res_all[c]);
+    } else {
+      epi_load_resid(p, row, n0, row_ok, res_all[0]);
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");   // bias_s / gate_s visible to the 4 epilogue warps
 
     mbar_wait(tmem_full_bar, 0);
@@ -185,8 +191,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.r = r_in_tile;
       stg.row0 = row0;
       stg.rows_valid = p.tiles_per_batch > 0 ? min(128, p.rows_per_batch - m_in_batch0) : min(128, p.M - row0);
-      epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s, gate_s, cs,
-                                              res0, p, n0, row, b_idx, row_ok, row_valid, stg);
+      if constexpr (kPreloadAll) {
+        epi_drain_tile_preloaded<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s,
+                                                          gate_s, cs, res_all, p, n0, row, b_idx, row_ok,
+                                                          row_valid, stg);
+      } else {
+        epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s, gate_s, cs,
+                                                res_all[0], p, n0, row, b_idx, row_ok, row_valid, stg);
+      }
     }
     tc_fence_before();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 8);

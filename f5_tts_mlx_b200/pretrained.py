@@ -88,8 +88,12 @@ def from_pretrained(cls, hf_model_name_or_path: str, convert_weights=None, quant
     vpath = path / "vocos.safetensors"
     if vpath.exists():
         vocoder = Vocos(VocosConfig(), device).load_weights(convert_vocos_upstream(load_file(str(vpath)))).decode
-    if (path / "duration_v2.safetensors").exists():
-        import warnings
-        warnings.warn("duration_v2.safetensors found but the DurationPredictor (duration.py) is not on the accelerated "
-                      "path yet: pass `duration=` explicitly")
-    return cls(transformer=dit, vocab_char_map=vocab, vocoder=vocoder)
+    duration_predictor = None
+    dpath = path / "duration_v2.safetensors"
+    if dpath.exists():                                                           # cfm.py:425-442
+        from .duration import DurationPredictor, DurationTransformer
+        duration_predictor = DurationPredictor(
+            transformer=DurationTransformer(dim=512, depth=8, heads=8, text_dim=512, ff_mult=2, conv_layers=2,
+                                            text_num_embeds=len(vocab) - 1),
+            vocab_char_map=vocab, device=device).load_weights(load_file(str(dpath)))
+    return cls(transformer=dit, vocab_char_map=vocab, vocoder=vocoder, duration_predictor=duration_predictor)

@@ -55,7 +55,17 @@ for (i, n, st, en, mma0, mmal, epi0) in rows:
     prev_end = en
 # skip precompute GEMMs: find the first call with 240 ctas? print a window of the second forward
 k0 = 11 + 92          # precompute (10 GEMMs + mod table = 10) ... approximate: print from there
-for o in out[k0:k0 + 40]:
+for o in out[k0:k0 + 12]:
     print(f"call {o[0]:4d} ctas {o[1]:4d} t={o[2]:9.1f}us dur={o[3]:6.2f}us gap_before={o[4]:6.2f}us mma0={o[5]:5.2f} mma_last={o[6]:5.2f}")
+NAMES = ["start", "setup", "pdl_wait", "tma0", "tma_last", "mma0", "mma_last", "epi0", "epi_end", "exit"]
+print("     " + " ".join(f"{n:>9s}" for n in NAMES))
+for (i, n, *_rest) in rows[k0 + 30:k0 + 38]:
+    m = t[i][:, 0] > 0
+    st0 = t[i][m][:, 0].min()
+    rel = (t[i][m] - st0) / 1e3
+    rel[t[i][m] == 0] = np.nan
+    print(f"call {i} ctas {n}")
+    print("mean " + " ".join(f"{np.nanmean(rel[:, k]):9.2f}" for k in range(10)))
+    print("max  " + " ".join(f"{np.nanmax(rel[:, k]):9.2f}" for k in range(10)))
 durs = np.array([o[3] for o in out[k0:k0 + 92]]); gaps = np.array([o[4] for o in out[k0:k0 + 92]])
 print("one forward (92 GEMMs): sum dur", durs.sum(), "us; sum gaps (incl. LN/attn/launch)", gaps.sum(), "us")
