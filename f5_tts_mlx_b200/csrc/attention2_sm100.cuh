@@ -66,7 +66,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   const int num_kv = (kv_len + 127) >> 7;
   const bool g1_active = q0 + 128 < p.N;   // second query tile has at least one real row
 
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
@@ -251,6 +250,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         mbar_arrive(&p_full[g]);
       }
       // epilogue: O / l
+      pdl_launch_dependents();
       mbar_wait(&pv_done[g], (num_kv - 1) & 1);
       tc_fence_after();
       const int n = q0 + g * 128 + r;

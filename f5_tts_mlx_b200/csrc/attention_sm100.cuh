@@ -63,7 +63,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
   kv_len = min(max(kv_len, 1), p.N);
   const int num_kv = (kv_len + 127) >> 7;
 
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
@@ -233,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
       tc_fence_before();
     }
     // epilogue: normalise, bf16, heads merged
+    pdl_launch_dependents();
     const int n = q0 + r;
     if (n < p.N) {
       const float inv = 1.f / l_run;

@@ -121,7 +121,6 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int pair_tiles_per_batch = p.tiles_per_batch;   // in units of 256-row pair tiles
 
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 0);
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -254,6 +253,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
+      if (t + num_clusters >= total_tiles) pdl_launch_dependents();   // last tile of this CTA: see gemm_sm100.cuh
       if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
       EpiStage stg;
       stg.buf = smem + S::kStageOutOffset;

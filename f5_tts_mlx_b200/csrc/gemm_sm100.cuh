@@ -72,7 +72,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   // ---- one-time setup (overlaps the predecessor kernel under PDL) ----
   const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
   if (threadIdx.x == 0) ts_mark(p, cta_lin, 0);
-  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -182,6 +181,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // PDL: the main loop is done — let the next kernel of the stream start its prologue (barrier
+    // init, TMEM alloc, descriptor prefetch) under this epilogue; it still waits (pdl_wait) for this
+    // grid to complete before touching memory.  (Triggering at kernel start measured SLOWER.)
+    pdl_launch_dependents();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 7);
     {
       // all MMAs have retired (tmem_full), so the operand ring is idle: its first 32 KB stage the stores
