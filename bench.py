@@ -98,6 +98,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic() -> dict:
+    """DRAM bytes per launch of the dominant (GEMM) kernels from the committed `ncu --set full`
+    capture of this workload (profiles/*_ncu_full.json, see tools/profile.sh); None if absent."""
+    import glob, re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full.json")))
+    if not files:
+        return {"traffic": None}
+    try:
+        d = json.load(open(files[-1]))
+        vals = []
+        for rec in d.get("gemm", []):
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.match(r"([0-9.]+)\s*(\w*)", rec.get(k, "0 byte"))
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(2), 1)
+                tot += float(m.group(1)) * scale
+            vals.append(tot)
+        if not vals:
+            return {"traffic": None}
+        return {"traffic": sum(vals) / len(vals), "traffic_note": f"mean DRAM read+write bytes per launch over the "
+                f"{len(vals)} GEMM launches captured in {os.path.basename(files[-1])} (cold cache under ncu)"}
+    except Exception as e:  # pragma: no cover
+        return {"traffic": None, "traffic_note": f"unreadable profile: {e}"}
+
+
 def peaks() -> dict:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -329,14 +354,14 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     n_fwd = O.dit_forwards_per_sample(args.ode_steps, args.method, args.cfg)
     alg_flops_step = n_fwd * O.dit_forward_flops(N, ocfg) * B
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"], "traffic": None,
+            "frac": achieved / pk["bf16_tflops"], **ncu_traffic(),
             "kernel": "gemm_bf16_tn_kernel (tcgen05, all shapes of one step)",
             "of": pk["source"],
             "gemm_share_of_step_device_time": g["ms"] / total_ms if total_ms else None,
             "attention": {"achieved": a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0,
                           "share_of_step_device_time": a["ms"] / total_ms if total_ms else None},
             "whole_step": {"algorithmic_tflop": alg_flops_step / 1e12,
-                           "achieved_tflops": alg_flops_step * world / (ms_total / args.steps * 1e-3) / 1e12,
+                           "achieved_tflops_per_gpu": alg_flops_step / (ms_total / args.steps * 1e-3) / 1e12,
                            "frac": alg_flops_step / (ms_total / args.steps * 1e-3) / 1e12 / pk["bf16_tflops"]}}
 
     # CPU baseline beside it (bounded sample)

@@ -24,8 +24,8 @@ struct Attn2Smem {
   static constexpr int kV = kK + 2 * 16384;           // 2 stages
   static constexpr int kP = kV + 2 * 16384;           // 2 groups x 32 KB
   static constexpr int kBar = kP + 2 * 32768;
-  // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2]
-  static constexpr int kNumBars = 15;
+  // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done[2], s_free[2]
+  static constexpr int kNumBars = 17;
   static constexpr int kTotal = kBar + kNumBars * 8 + 16;
 };
 
@@ -54,6 +54,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   uint64_t* s_full = bars + 9;    // [2] per group
   uint64_t* p_full = bars + 11;   // [2] per group
   uint64_t* pv_done = bars + 13;  // [2] per group
+  uint64_t* s_free = bars + 15;   // [2] per group: the softmax group holds S_j in registers
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Attn2Smem::kNumBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,6 +78,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 128);
     }
     fence_mbar_init();
   }
@@ -147,8 +149,22 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
       const int s = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const bool more = j + 1 < num_kv;
+      // S_g(j+1) as soon as group g has pulled S_g(j) into registers (s_free) — it is then ready by the
+      // time the group finishes exponentiating tile j, instead of being issued behind PV_g(j)
+      if (more) {
+        mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&s_free[g], j & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_S(g, s ^ 1);
+            tc_commit(&s_full[g]);
+            if (g == ngroups - 1) tc_commit(&k_empty[s ^ 1]);
+          }
+          __syncwarp();
+        }
+      }
       mbar_wait(&v_full[s], ph);
-      if (more) mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
       for (int g = 0; g < ngroups; ++g) {
         mbar_wait(&p_full[g], j & 1);
         tc_fence_after();
@@ -156,11 +172,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
           issue_PV(g, s, j > 0);
           tc_commit(&pv_done[g]);
           if (g == ngroups - 1) tc_commit(&v_empty[s]);
-          if (more) {
-            issue_S(g, s ^ 1);
-            tc_commit(&s_full[g]);
-            if (g == ngroups - 1) tc_commit(&k_empty[s ^ 1]);
-          }
         }
         __syncwarp();
       }
@@ -191,6 +202,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         tmem_ld32(tmem_S + 64, sv + 64);
         tmem_ld32(tmem_S + 96, sv + 96);
         tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);          // S_g may be overwritten by the next tile's scores
         const int kv0 = j * 128;
         if (kv0 + 128 > kv_len) {
 #pragma unroll
