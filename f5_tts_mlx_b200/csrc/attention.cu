@@ -3,6 +3,7 @@
 
 #include "attention_sm100.cuh"
 #include "attention2_sm100.cuh"
+#include "attention3_sm100.cuh"
 #include "host_common.h"
 
 extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
@@ -32,9 +33,20 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
                                        AttnSmem::kTotal));
     F5_CHECK_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Attn2Smem::kTotal));
+    F5_CHECK_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Attn3Smem::kTotal));
     const char* v = getenv("F5_ATTN_VARIANT");
     if (v && v[0] == '1') variant = 1;
+    if (v && v[0] == '3') variant = 3;
     attr_set = true;
+  }
+  if (variant == 3) {
+    dim3 grid3(cdiv(frames, 256), heads, batch);
+    ProfScope ps3(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
+                  2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
+    F5_CHECK_CUDA(launch_kernel(attn3_fwd_kernel, grid3, dim3(640), Attn3Smem::kTotal,
+                                reinterpret_cast<cudaStream_t>(stream_), tm, p));
+    return 0;
   }
   if (variant == 2) {
     dim3 grid2(cdiv(frames, 256), heads, batch);

@@ -1,4 +1,3 @@
 export PYTHONPATH=.
-python tests/gpu_checks/check_attention.py 2>&1 | tail -12
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('B1: ms/step', d['ms_per_step'], 'value', d['value'], 'e2e', d['e2e']['value'])"
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+F5_ATTN_VARIANT=3 python tests/gpu_checks/check_attention.py 2>&1 | tail -12
+F5_ATTN_VARIANT=3 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('B1 attn v3: ms/step', d['ms_per_step'], 'value', d['value'])"

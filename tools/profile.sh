@@ -4,11 +4,12 @@
 set -x
 OUT=gpurun_out
 mkdir -p $OUT
+rm -f $OUT/prof_*.ncu-rep $OUT/launches.csv
 # every launch of precompute + the first DiT evaluations (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file $OUT/launches.csv \
     python bench.py --profile-run > $OUT/ncu_launches.log 2>&1
-# top kernels, full set, 2 launches each, skipping the precompute launches
-ncu --set full --clock-control none --import-source on -k regex:gemm -s 40 -c 6 -o $OUT/prof_gemm -f \
+# top kernels, full set, skipping the precompute launches: one block's QKV (pair kernel), out-proj, FF1, FF2
+ncu --set full --clock-control none --import-source on -k regex:gemm -s 44 -c 5 -o $OUT/prof_gemm -f \
     python bench.py --profile-run > $OUT/ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attn -s 2 -c 2 -o $OUT/prof_attn -f \
     python bench.py --profile-run > $OUT/ncu_attn.log 2>&1
