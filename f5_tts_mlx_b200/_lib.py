@@ -75,6 +75,7 @@ SYMBOLS: dict[str, tuple] = {
     "f5_prof_summary": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
     "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "f5_debug_gemm_ts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
+    "f5_debug_attention_ts": (C.c_int, [C.c_void_p]),
     "f5_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "f5_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -3,16 +3,25 @@
 // Same contract as attention_sm100.cuh (replaces mx.fast.scaled_dot_product_attention, dit.py:166).
 //
 //   warp 0      TMA: Q0,Q1 once; K/V 128-key tiles in 2-stage rings
-//   warp 1      MMA issuer, order  S0_0 S1_0 | PV0_j S0_{j+1} PV1_j S1_{j+1} | ...
+//   warp 1, 2   MMA issuers, one per query tile g (order per tile:  S_g(0) | S_g(j+1) PV_g(j) | ...)
 //               S_g = Q_g K^T (M128 N128 K64) -> TMEM S_g;  O_g += P_g V (M128 N64 K128) -> TMEM O_g
-//   warps 2-3   idle (complete warpgroup 0, which hands its registers to the softmax warpgroups)
+//   warp 3      idle (completes warpgroup 0, which hands its registers to the softmax warpgroups)
 //   warps 4-7   softmax group 0 (thread = query row of tile 0), 224 registers via setmaxnreg
 //   warps 8-11  softmax group 1 (tile 1)
-// While group 0 exponentiates S0_j the tensor cores compute S1_j / PV1_{j-1}, and vice versa.
 // The running max used for exponentiation (m_used) is only advanced — and O_g/l rescaled in TMEM —
 // when the true row max has grown by more than 2^8 (any thread of the warp), so the common case
 // has no accumulator traffic at all; the final O/l is exact either way.
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).  smem 160 KB -> one CTA per SM.
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512) (kPT).
+//
+// What the r01 probes (f5_debug_attention_ts, tests/gpu_checks/check_attn_timeline.py) showed, per 128-key
+// tile of both groups, and what was done about it:
+//   * one issuing thread for both tiles = a 3600-clk serial chain of 24 MMAs + 6 commits (short bursts cost
+//     55-130 clk per MMA to issue, tools/microbench/mma_issue.cu)            -> one issuer warp per tile;
+//   * 256 KB of smem traffic (2048 clk at 128 B/clk) next to the 2048-clk MUFU floor
+//                                                                          -> P in TMEM (kPT), 128 KB;
+//   * both groups in lockstep, XU idle during their TMEM loads / row max    -> hand-off barriers: a group
+//     starts its exponentials when the other one is half way through its own.
+// B2 N937 H16: 22.1 -> 18.4 us; B128: 1153 -> 990 us (cuDNN SDPA on the same box: 17.3 / 651 us).
 #pragma once
 #include "attention_sm100.cuh"
 
@@ -42,6 +51,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// kPT: P goes to TMEM columns [384,448) / [448,512) and the PV MMA reads it from there (A operand in tensor
+// memory) instead of a swizzled smem tile.  Timeline probes (r01) showed the SS variant bound by shared-memory
+// bandwidth: per key tile the two groups moved 256 KB through smem (K/V fill 32, S operands 64, PV operands
+// 96, P stores 64) = 2048 clk at 128 B/clk, on top of the 2048 clk MUFU floor; with P in TMEM it is 128 KB.
+template <bool kPT>
 __global__ void __launch_bounds__(384, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -66,15 +80,21 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   kv_len = min(max(kv_len, 1), p.N);
   const int num_kv = (kv_len + 127) >> 7;
   const bool g1_active = q0 + 128 < p.N;   // second query tile has at least one real row
+  const bool handoff = g1_active && p.handoff;
+  const bool probe = p.ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                     (warp == 1 || warp == 2 || warp == 4 || warp == 8);
+  auto stamp = [&](int role, int j, int slot) {
+    if (probe && j < 64) p.ts[(role * 64 + j) * 8 + slot] = (unsigned long long)clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], g1_active ? 2 : 1);   // released by every active issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], g1_active ? 2 : 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&pv_done[i], 1);
@@ -111,67 +131,71 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         tma_load_3d(smem + Attn2Smem::kV + s * 16384, &tma_qkv, &v_full[s], 2 * HD + h * 64, j * 128, b);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: one warp per query tile =====================
+    // (r01 timeline: with ONE issuing thread for both tiles the 24 MMAs + 6 commits of a key tile were a
+    // serial chain of ~3600 clk — short MMA bursts cost 55-85 clk each to issue, tools/microbench/mma_issue.cu —
+    // and every group's P·V sat behind the other group's barriers.  Two issuers decouple the groups.)
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-    const uint32_t sQ = smem_u32(smem + Attn2Smem::kQ);
-    const uint32_t sPbase = smem_u32(smem + Attn2Smem::kP);
-    const int ngroups = g1_active ? 2 : 1;
-    auto issue_S = [&](int g, int stage) {
+    const int g = warp - 1;
+    const uint32_t sQ = smem_u32(smem + Attn2Smem::kQ) + g * 16384;
+    const uint32_t sP = smem_u32(smem + Attn2Smem::kP) + g * 32768;
+    const uint32_t tS = tmem_base + g * 128, tO = tmem_base + 256 + g * 64, tP = tmem_base + 384 + g * 64;
+    auto issue_S = [&](int stage) {
       const uint32_t sK = smem_u32(smem + Attn2Smem::kK + stage * 16384);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_f16_ss(tmem_base + g * 128, umma_desc_sw128(sQ + g * 16384 + k * 32, 16, 1024),
-                    umma_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_f16_ss(tS, umma_desc_sw128(sQ + k * 32, 16, 1024), umma_desc_sw128(sK + k * 32, 16, 1024), idesc_s,
+                    k != 0);
     };
-    auto issue_PV = [&](int g, int stage, bool acc) {
+    auto issue_PV = [&](int stage, bool acc) {
       const uint32_t sV = smem_u32(smem + Attn2Smem::kV + stage * 16384);
-      const uint32_t sP = sPbase + g * 32768;
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_f16_ss(tmem_base + 256 + g * 64,
-                    umma_desc_sw128(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    umma_desc_sw128(sV + k * 2048, 16384, 1024), idesc_o, (acc || k != 0) ? 1u : 0u);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (lane == 0) {
-      for (int g = 0; g < ngroups; ++g) {
-        issue_S(g, 0);
-        tc_commit(&s_full[g]);
+      for (int k = 0; k < 8; ++k) {
+        if constexpr (kPT)
+          umma_f16_ts(tO, tP + k * 8, umma_desc_sw128(sV + k * 2048, 16384, 1024), idesc_o,
+                      (acc || k != 0) ? 1u : 0u);
+        else
+          umma_f16_ss(tO, umma_desc_sw128(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      umma_desc_sw128(sV + k * 2048, 16384, 1024), idesc_o, (acc || k != 0) ? 1u : 0u);
       }
-      tc_commit(&k_empty[0]);
-    }
-    __syncwarp();
-    for (int j = 0; j < num_kv; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const bool more = j + 1 < num_kv;
-      // S_g(j+1) as soon as group g has pulled S_g(j) into registers (s_free) — it is then ready by the
-      // time the group finishes exponentiating tile j, instead of being issued behind PV_g(j)
-      if (more) {
-        mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
-        for (int g = 0; g < ngroups; ++g) {
+    };
+    if (g == 0 || g1_active) {
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (lane == 0) {
+        issue_S(0);
+        tc_commit(&s_full[g]);
+        tc_commit(&k_empty[0]);
+      }
+      __syncwarp();
+      for (int j = 0; j < num_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        // S_g(j+1) as soon as the group has pulled S_g(j) into registers (s_free): it is ready by the time
+        // the group finishes exponentiating tile j
+        if (j + 1 < num_kv) {
+          mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
           mbar_wait(&s_free[g], j & 1);
           tc_fence_after();
           if (lane == 0) {
-            issue_S(g, s ^ 1);
+            stamp(2, j, g);
+            issue_S(s ^ 1);
             tc_commit(&s_full[g]);
-            if (g == ngroups - 1) tc_commit(&k_empty[s ^ 1]);
+            tc_commit(&k_empty[s ^ 1]);
           }
           __syncwarp();
         }
-      }
-      mbar_wait(&v_full[s], ph);
-      for (int g = 0; g < ngroups; ++g) {
+        mbar_wait(&v_full[s], ph);
         mbar_wait(&p_full[g], j & 1);
         tc_fence_after();
         if (lane == 0) {
-          issue_PV(g, s, j > 0);
+          stamp(2, j, 3 + g);
+          issue_PV(s, j > 0);
           tc_commit(&pv_done[g]);
-          if (g == ngroups - 1) tc_commit(&v_empty[s]);
+          tc_commit(&v_empty[s]);
         }
         __syncwarp();
       }
@@ -187,14 +211,18 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
       const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
       const uint32_t tmem_S = tmem_base + g * 128 + lane_addr;
       const uint32_t tmem_O = tmem_base + 256 + g * 64 + lane_addr;
+      const uint32_t tmem_P = tmem_base + 384 + g * 64 + lane_addr;
       uint8_t* sP = smem + Attn2Smem::kP + g * 32768;
       constexpr float kLog2e = 1.4426950408889634f;
       float m_run = -INFINITY;   // true running max
       float m_used = 0.f;        // max used for the exponentials / O / l (lags m_run by <= 8 in log2 units)
       float l_run = 0.f;
+      if (g == 1 && handoff) asm volatile("bar.arrive 2, 256;\n" ::: "memory");   // group 0 goes first
 
       for (int j = 0; j < num_kv; ++j) {
+        stamp(g, j, 0);
         mbar_wait(&s_full[g], j & 1);
+        stamp(g, j, 1);
         tc_fence_after();
         uint32_t sv[128];
         tmem_ld32(tmem_S + 0, sv);
@@ -204,6 +232,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&s_free[g]);          // S_g may be overwritten by the next tile's scores
+        stamp(g, j, 2);
         const int kv0 = j * 128;
         if (kv0 + 128 > kv_len) {
 #pragma unroll
@@ -219,8 +248,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
           mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
         }
         m_run = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        // P_g smem and O_g TMEM are free once PV_g(j-1) has completed
+        stamp(g, j, 3);
+        // P_g and O_g are free once PV_g(j-1) has completed.  (Deferring this wait into the exponential loop
+        // and splitting the TMEM load around the row max both measured slower: they break the MUFU schedule.)
         if (j > 0) mbar_wait(&pv_done[g], (j - 1) & 1);
+        stamp(g, j, 4);
         bool grow = (j == 0) || ((m_run - m_used) * kLog2e > 8.f);
         if (__any_sync(0xffffffffu, grow)) {
           if (j > 0) {
@@ -242,25 +274,61 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
           m_used = m_run;
         }
         const float mb = m_used * kLog2e;
+        // MUFU hand-off: the two groups take turns in the exponential loop (named barriers 2/3, 128 + 128
+        // threads), so one group's TMEM loads / row max / barrier traffic run under the other's MUFU work
+        // instead of both idling the XU pipe at the same time (they otherwise fall into lockstep behind
+        // the single MMA warp)
+        if (handoff) {
+          if (g == 0) asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          else asm volatile("bar.sync 3, 256;\n" ::: "memory");
+        }
         // (a packed FFMA2/FADD2 + 25 % polynomial-exp2 variant of this loop measured SLOWER on B200:
         // 24.9 us vs 21.5 us at B2 N937 H16 — kept out until the register-pair moves are understood)
+        stamp(g, j, 5);
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
         uint8_t* prow = sP + r * 128;
+        uint32_t pk_lo[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int c = 0; c < 16; ++c) {   // 16 chunks of 8 probabilities = 16 bytes
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), kLog2e, -mb));
           l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
-          const int chunk = (c & 7) ^ (r & 7);
-          *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + chunk * 16) =
-              make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                         pack_bf16x2(e[6], e[7]));
+          if (c == 7 && p.handoff == 2 && handoff) {   // early release: the other group may start at half time
+            if (g == 0) asm volatile("bar.arrive 3, 256;\n" ::: "memory");
+            else if (j + 1 < num_kv) asm volatile("bar.arrive 2, 256;\n" ::: "memory");
+          }
+          if constexpr (kPT) {
+            const uint32_t pk[4] = {pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                                    pack_bf16x2(e[6], e[7])};
+            if (c & 1) {
+              const uint32_t both[8] = {pk_lo[0], pk_lo[1], pk_lo[2], pk_lo[3], pk[0], pk[1], pk[2], pk[3]};
+              tmem_st8(tmem_P + (c >> 1) * 8, both);
+            } else {
+              pk_lo[0] = pk[0]; pk_lo[1] = pk[1]; pk_lo[2] = pk[2]; pk_lo[3] = pk[3];
+            }
+          } else {
+            const int chunk = (c & 7) ^ (r & 7);
+            *reinterpret_cast<uint4*>(prow + (c >> 3) * 16384 + chunk * 16) =
+                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
+                           pack_bf16x2(e[6], e[7]));
+          }
         }
         l_run += (l0 + l1) + (l2 + l3);
-        tc_fence_before();
-        fence_proxy_async_smem();
+        stamp(g, j, 6);
+        if (handoff && p.handoff != 2) {
+          if (g == 0) asm volatile("bar.arrive 3, 256;\n" ::: "memory");
+          else if (j + 1 < num_kv) asm volatile("bar.arrive 2, 256;\n" ::: "memory");
+        }
+        if constexpr (kPT) {
+          tmem_wait_st();
+          tc_fence_before();
+        } else {
+          tc_fence_before();
+          fence_proxy_async_smem();
+        }
         mbar_arrive(&p_full[g]);
+        stamp(g, j, 7);
       }
       // epilogue: O / l
       pdl_launch_dependents();

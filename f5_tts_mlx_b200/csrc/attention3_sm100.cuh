@@ -173,7 +173,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   }
   } else {
     // ===================== softmax groups =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n");
     const int g = (warp - 4) >> 3;            // 8 warps per query tile
     const int hh = ((warp - 4) >> 2) & 1;     // which 64-column half of the key tile / 32-column half of O
     if (g == 0 || g1_active) {

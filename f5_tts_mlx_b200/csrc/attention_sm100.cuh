@@ -27,6 +27,8 @@ struct AttnParams {
   const int* kv_len;       // [B] valid keys per utterance, or null (= N)
   __nv_bfloat16* out;      // [B*N, H*64]
   int ldo;
+  unsigned long long* ts;  // debug: [3 roles][64 tiles][8 slots] SM-clock stamps of CTA (0,0,0), or null
+  int handoff;             // v2: softmax groups alternate in the exponential loop (F5_ATTN_HANDOFF=0 disables)
 };
 
 struct AttnSmem {

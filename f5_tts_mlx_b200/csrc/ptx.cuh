@@ -168,6 +168,23 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: A (M x K, K-major) read from tensor memory — row m in lane m, two
+// 16-bit K elements per 32-bit column (K = 16 -> 8 columns at `tmem_a`)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // tcgen05.ld 32 lanes x 32 bit, x16 / x32 columns: thread t of warp w reads TMEM lane
 // 32*(w%4)+t, columns [col, col+n).  taddr = (lane << 16) | col.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {

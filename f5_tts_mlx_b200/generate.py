@@ -83,7 +83,12 @@ def generate(
     quantization_bits: Optional[int] = None,
     output_path: Optional[str] = None,
     f5tts: Optional[F5TTS] = None,
+    batch_sentences: bool = False,
 ):
+    """generate.py:113-244.  Extensions: `f5tts` reuses a loaded model; `batch_sentences=True` runs all
+    sentences as ONE ragged `sample()` batch instead of the reference's serial loop (SURVEY §8f row 2;
+    numerically it differs from the serial loop only through the reference's own padding caveat — GRN
+    statistics and the ODE on padded frames see the batch-maximum length)."""
     if f5tts is None:
         f5tts = F5TTS.from_pretrained(model_name, quantization_bits=quantization_bits)
     dev = f5tts.transformer.device
@@ -108,6 +113,31 @@ def generate(
     frames = None
     if duration is not None:
         frames = int(duration * FRAMES_PER_SEC)
+    if batch_sentences and len(todo) > 1:
+        if duration is None and not estimate_duration and f5tts._duration_predictor is None:
+            raise ValueError("Duration must be provided or a duration predictor must be set.")
+        mel = f5tts._mel_spec(audio_d)                                    # (1, n_ref, 100), computed once
+        texts = convert_char_to_pinyin([ref_audio_text + " " + s_ for s_ in todo])
+        if duration is None and estimate_duration:
+            durs = torch.tensor([int(estimated_duration(audio, ref_audio_text, s_, speed) * FRAMES_PER_SEC) for s_ in todo])
+        elif duration is None:
+            durs = None
+        else:
+            durs = torch.full((len(todo),), frames)
+        cond = mel.repeat(len(todo), 1, 1)
+        vocoder, f5tts._vocoder = f5tts._vocoder, None                    # decode per utterance at its own length
+        try:
+            out, _ = f5tts.sample(cond, text=texts, duration=durs, steps=steps, method=method, speed=speed,
+                                  cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, seed=seed,
+                                  return_trajectory=False)
+        finally:
+            f5tts._vocoder = vocoder
+        plan = f5tts.last_plan
+        lens_i = plan.session.seq_len[: len(todo)].tolist() if plan.session.seq_len is not None else [out.shape[1]] * len(todo)
+        for i in range(len(todo)):
+            wave_i = vocoder(out[i:i + 1, : lens_i[i]]) if vocoder is not None else out[i, : lens_i[i]]
+            waves.append(wave_i[audio.shape[0]:] if vocoder is not None else wave_i)
+        todo = []
     for sentence in todo:
         if duration is None and estimate_duration:
             frames = int(estimated_duration(audio, ref_audio_text, sentence if not single else generation_text, speed)

@@ -116,6 +116,9 @@ int f5_debug_gemm_ts(void* base, int64_t stride_bytes, int32_t max_calls);
 int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch,
                      int32_t frames, int32_t heads, int32_t head_dim, const int32_t* kv_len,
                      void* stream);
+/* debug aid: while `base` is non-NULL, attention launches write SM-clock stamps of CTA (0,0,0) into it:
+   uint64 [3 roles (softmax group 0, group 1, MMA warp)][64 key tiles][8 slots]; NULL switches it off. */
+int f5_debug_attention_ts(void* base);
 
 /* ------------------------------------------------------------------------------------------ *
  * HBM-bound pieces.

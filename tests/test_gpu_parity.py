@@ -298,3 +298,41 @@ def test_sample_with_duration_predictor(gate):
     assert abs(out.shape[1] - expect) <= 1 and torch.isfinite(out).all()
     with pytest.raises(ValueError):
         F5TTS(model).sample(cond.to(dev), text, None, steps=2, method="euler")
+
+
+def test_generate_end_to_end_serial_and_batched_sentences(tmp_path):
+    """generate.py:113-244 through the package's own `generate()`: wav in -> wav out on the base architecture
+    (random weights), serial per-sentence loop (the reference's) and the one-ragged-batch extension.  Checks
+    the bookkeeping the reference does around sample(): RMS normalisation, sentence split, estimated duration,
+    reference-audio stripping, concatenation, 16-bit wav writing."""
+    from f5_tts_mlx_b200 import F5TTS
+    from f5_tts_mlx_b200 import generate as G
+    torch.manual_seed(0)
+    ref = 0.02 * torch.randn(2 * 24000)                                      # quiet clip -> exercises the RMS branch
+    G.write_wav(str(tmp_path / "ref.wav"), ref)
+    text, ref_text = "Hello there. This is a test!", "some reference text."
+    n_ref = ref.shape[0]
+    expect = 0
+    f5 = F5TTS.from_pretrained("random")
+    for s in G.split_sentences(text):
+        frames = int(G.estimated_duration(ref, ref_text, s) * G.FRAMES_PER_SEC)
+        frames = max(frames, n_ref // 256 + 1)
+        expect += f5._vocoder.__self__.out_len(frames) - n_ref          # un-trimmed ISTFT: (frames-1)*256 + 1024
+    waves = {}
+    for batched in (False, True):
+        out = tmp_path / f"out{int(batched)}.wav"
+        w = G.generate(text, estimate_duration=True, ref_audio_path=str(tmp_path / "ref.wav"), ref_audio_text=ref_text,
+                       steps=4, method="euler", seed=7, output_path=str(out), f5tts=f5, batch_sentences=batched)
+        assert w.ndim == 1 and torch.isfinite(w).all() and float(w.abs().max()) > 0
+        assert abs(w.shape[0] - expect) <= 3 * 256, (w.shape, expect)
+        back, sr = G.read_wav(str(out))
+        assert sr == 24000 and back.shape[0] == w.shape[0]
+        waves[batched] = w
+    assert waves[False].shape == waves[True].shape
+    with pytest.raises(ValueError):                                           # generate.py:147-148
+        import wave as wavmod
+        with wavmod.open(str(tmp_path / "bad.wav"), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(b"\0\0" * 100)
+        G.generate(text, duration=3.0, ref_audio_path=str(tmp_path / "bad.wav"), f5tts=f5)
+    with pytest.raises(ValueError):                                           # no duration, no estimate, no predictor
+        G.generate(text, ref_audio_path=str(tmp_path / "ref.wav"), f5tts=f5)

@@ -155,3 +155,50 @@ def test_shard_range_partitions(n, w):
     parts = [shard_range(n, w, r) for r in range(w)]
     assert [i for p in parts for i in p] == list(range(n))
     assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_from_pretrained_local_directory_roundtrip(tmp_path):
+    """cfm.py:404-520 against a local directory: MLX-named and upstream-named safetensors both load into
+    the same packed weights (key rename + conv transposes of cfm.py:477-508), vocab gives text_num_embeds =
+    len(vocab) - 1, Vocos weights are picked up, the duration checkpoint builds a predictor.  CPU only."""
+    from safetensors.torch import save_file
+    from f5_tts_mlx_b200 import F5TTS
+    from f5_tts_mlx_b200.weights import BASE_CONFIG, random_duration_weights, random_vocos_weights
+    import f5_tts_mlx_b200.pretrained as PT
+    vocab_chars = [chr(ord("a") + i) for i in range(10)]
+    (tmp_path / "vocab.txt").write_text("\n".join(vocab_chars) + "\n")          # trailing '' entry like the real file
+    # a SMALL stand-in for the base architecture is not possible (from_pretrained hard-codes it, cfm.py:459-469),
+    # so build the real shapes once with tiny text table (len(vocab) - 1 = 10)
+    cfg = type(BASE_CONFIG)(text_num_embeds=10)
+    W = random_dit_weights(cfg, seed=3)
+    save_file({k: v.contiguous() for k, v in W.items() if "inv_freq" not in k}, str(tmp_path / "model_v1.safetensors"))
+    vw = {k[len("vocos."):]: v for k, v in random_vocos_weights().items()}
+    up = {}
+    for k, v in vw.items():                                                    # upstream torch layouts (O, I, K)
+        up[k] = v.transpose(1, 2).contiguous() if (k.endswith("dwconv.weight") or k == "backbone.embed.weight") else v.contiguous()
+    save_file(up, str(tmp_path / "vocos.safetensors"))
+    save_file({k: v.contiguous() for k, v in random_duration_weights(text_num_embeds=10, seed=4).items()},
+              str(tmp_path / "duration_v2.safetensors"))
+    f5 = PT.from_pretrained(F5TTS, str(tmp_path), convert_weights=False, device="cpu")
+    assert f5.transformer.config.text_num_embeds == 10 and f5._vocoder is not None and f5._duration_predictor is not None
+    got = f5.transformer.packed.view("blk5.ff1_w").float()
+    assert torch.equal(got, W["transformer.transformer_blocks.5.ff.ff.layers.0.layers.0.weight"].bfloat16().float())
+    # the same checkpoint in upstream naming / layouts goes through convert_upstream_keys
+    inv = {}
+    for k, v in W.items():
+        if "inv_freq" in k:
+            continue
+        k2 = (k.replace(".to_out.layers", ".to_out").replace(".text_blocks.layers", ".text_blocks")
+               .replace(".ff.ff.layers.0.layers.0", ".ff.ff.0.0").replace(".ff.ff.layers.2", ".ff.ff.2")
+               .replace(".time_mlp.layers", ".time_mlp").replace(".conv1d.layers", ".conv1d"))
+        if ".dwconv.weight" in k or ".conv1d.layers.0.weight" in k or ".conv1d.layers.2.weight" in k:
+            v = v.transpose(1, 2)
+        inv["ema_model." + k2] = v.contiguous()
+    inv["ema_model.mel_spec.mel_stft.window"] = torch.zeros(4)
+    save_file(inv, str(tmp_path / "model_v1.safetensors"))
+    f5b = PT.from_pretrained(F5TTS, str(tmp_path), device="cpu")
+    assert torch.equal(f5b.transformer.packed.buffer, f5.transformer.packed.buffer)
+    with pytest.raises(NotImplementedError):
+        PT.from_pretrained(F5TTS, str(tmp_path), quantization_bits=4)
+    with pytest.raises(ValueError):
+        PT.from_pretrained(F5TTS, str(tmp_path / "missing"))
