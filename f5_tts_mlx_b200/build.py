@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
         if (not force) and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_mtime):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("F5_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

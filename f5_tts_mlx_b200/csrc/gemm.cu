@@ -23,7 +23,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(192), S::kTotal, stream, ta, tb, p));
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, p));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -70,7 +70,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(256), S::kTotal, stream, ta, tb, p, n_tiles, total_tiles));
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), S::kTotal, stream, ta, tb, p, n_tiles, total_tiles));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -203,10 +203,10 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     cudaStream_t stream2 = reinterpret_cast<cudaStream_t>(stream_);
     const bool rope2 = a->rope != nullptr;
     if (bn2 == 192)
-      return dispatch_epi2<192, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+      return dispatch_epi2<192, 5>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
     if (bn2 == 256)
-      return dispatch_epi2<256, 5>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
-    return dispatch_epi2<128, 7>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+      return dispatch_epi2<256, 4>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+    return dispatch_epi2<128, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
   }
 
   int bn = a->tile_n;

@@ -93,11 +93,11 @@ struct Gemm2Smem {
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN])
   static constexpr int kStageOutOffset = (kColsOffset + 4 * BN * 4 + 127) & ~127;   // 2 x 16 KB store staging
-  static constexpr int kTotal = kStageOutOffset + 32768 + 1024;  // + align slack
+  static constexpr int kTotal = kStageOutOffset + 2 * 32768 + 1024;  // 2 epilogue groups x (2 x 16 KB) + align slack
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
                      const int n_tiles, const int total_tiles) {
@@ -130,7 +130,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);   // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty_bar[i], 16);   // 8 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -147,6 +147,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   pdl_wait();
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 2);
 
+  // register hand-over (384 threads cap every thread at 168): warps 0-3 need few, the epilogue warps hold a
+  // row's RoPE table, residual and accumulator chunk.  128 x 40 + 256 x 232 <= 64 K registers.
+  // (setmaxnreg must sit INSIDE the role branches, or ptxas applies the small budget to everything.)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
@@ -212,8 +217,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       }
       if (lane == 0) ts_mark(p, blockIdx.x, 6);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     // ===================== epilogue (both CTAs) =====================
+    // two groups of 4 warps interleave the tile's 64-column units (see gemm_sm100.cuh: the epilogue is a
+    // latency chain; with K = 1024 one group needed longer per tile than the main loop)
+    const int grp = (warp - 4) >> 2;
+    const int et = ((warp - 4) & 3) * 32 + lane;
     const int lg = warp & 3;
     const int r_in_tile = (int)rank * 128 + lg * 32 + lane;   // row inside the 256-row pair tile
     int acount = 0;
@@ -244,20 +255,22 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       // operand staging for this tile (overlaps the MMAs still filling the accumulator)
       float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * 2 * BN;
       float* gate_s = bias_s + BN;
-      epi_stage_cols<BN>(p, n0, (warp - 4) * 32 + lane, bias_s, gate_s);
+      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s);   // both groups write the same values
       float2 cs[ROPE ? 32 : 1];
       epi_load_rope<ROPE>(p, pos, cs);
       float4 res0[8];
-      epi_load_resid(p, row, n0, row_ok, res0);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      epi_load_resid(p, row, n0 + grp * 64, row_ok, res0);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
       if (t + num_clusters >= total_tiles) pdl_launch_dependents();   // last tile of this CTA: see gemm_sm100.cuh
       if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
       EpiStage stg;
-      stg.buf = smem + S::kStageOutOffset;
-      stg.et = (warp - 4) * 32 + lane;
+      stg.buf = smem + S::kStageOutOffset + grp * 32768;
+      stg.et = et;
+      stg.bar_id = 1 + grp;
+      stg.probe_cta = blockIdx.x;
       stg.r = lg * 32 + lane;
       if (pair_tiles_per_batch > 0) {
         const int m0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
@@ -268,7 +281,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         stg.rows_valid = min(128, p.M - (int)stg.row0);
       }
       epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
-                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg);
+                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg, grp, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);

@@ -135,6 +135,8 @@ struct EpiStage {
   int r;                   // this thread's row inside the tile
   long long row0;          // global row of tile row 0
   int rows_valid;          // rows of the tile that exist
+  int bar_id;              // named barrier of this group of 4 epilogue warps (1 + group)
+  int probe_cta;           // debug (F5_EPI_PROBE builds): linear CTA id for sub-step stamps
 };
 
 template <bool OUT_BF16>
@@ -149,7 +151,7 @@ __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const Epi
       *reinterpret_cast<uint4*>(mine + ((j ^ sw) * 16)) =
           make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
     const int q = st.et & 3;
 #pragma unroll
@@ -166,7 +168,7 @@ __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const Epi
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(mine + ((j ^ sw) * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
     float* out = reinterpret_cast<float*>(p.out);
     const int q = st.et & 7;
 #pragma unroll
@@ -287,15 +289,17 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 }
 
 // Drains one accumulator tile of BN columns: TMEM base `tmem_acc` (lane group already applied).
+// (cc0, cc_step): this group of 4 warps takes the 64-column units cc0, cc0 + cc_step, ... (two groups
+// interleave units in the CTA-pair kernel); `res0` holds the residual of unit cc0's first 32 columns.
 template <int BN, int ACT, bool OUT_BF16, bool ROPE>
 __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* bias_s,
                                                const float* gate_s, const float2 (&cs)[ROPE ? 32 : 1],
                                                float4 (&res0)[8], const GemmParams& p, int n0, int row,
                                                int b_idx, bool row_ok, bool row_valid,
-                                               const EpiStage& st) {
+                                               const EpiStage& st, int cc0 = 0, int cc_step = 1) {
   float4 res1[8];
 #pragma unroll 1
-  for (int cc = 0; cc < BN / 64; ++cc) {
+  for (int cc = cc0; cc < BN / 64; cc += cc_step) {
     const int colA = n0 + cc * 64, colB = colA + 32;
     uint32_t acc[32];
     // chunk A (first half of the head): request chunk B's residual, then drain A
@@ -305,8 +309,8 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
     if (colA < p.N)   // uniform per CTA
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
                                         b_idx, row_ok, row_valid, st);
-    // chunk B: request the next pair's first residual, then drain B
-    if (cc + 1 < BN / 64) epi_load_resid(p, row, colA + 64, row_ok, res0);
+    // chunk B: request the next unit's first residual, then drain B
+    if (cc + cc_step < BN / 64) epi_load_resid(p, row, colA + 64 * cc_step, row_ok, res0);
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)
@@ -332,9 +336,15 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
     uint32_t acc[32];
     tmem_ld32(tmem_acc + cc * 64, acc);
     tmem_wait_ld();
+#ifdef F5_EPI_PROBE
+    if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 3);
+#endif
     if (colA < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
                                         b_idx, row_ok, row_valid, st);
+#ifdef F5_EPI_PROBE
+    if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 4);
+#endif
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)

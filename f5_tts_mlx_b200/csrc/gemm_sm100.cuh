@@ -38,8 +38,20 @@ struct GemmSmem {
   static constexpr int kTotal = kColsOffset + 2 * BN * 4 + 1024;  // + align slack
 };
 
+// Epilogue groups: 4 warps cover the 128 accumulator rows (TMEM lane quarter = warp % 4).  With 128-column
+// tiles a second group of 4 warps drains columns [64,128) while the first drains [0,64): in the one-wave
+// B=1 GEMMs the epilogue is a serial tail behind the main loop (in-situ timelines: 3.0-4.2 us of a 10-17 us
+// kernel with one group), and its cost is latency (TMEM load -> math -> staged store), not bandwidth.
+// (Only for the one-CTA-per-SM variant: with two co-resident CTAs 320 threads would leave 96 registers.)
+template <int BN, int kStages>
+struct GemmEpi {
+  static constexpr int kGroups = (BN >= 128 && kStages > 4) ? 2 : 1;
+  static constexpr int kThreads = 64 + 128 * kGroups;
+  static constexpr int kCols = BN / kGroups;          // columns per group
+};
+
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-__global__ void __launch_bounds__(192, (kStages > 4) ? 1 : 2)
+__global__ void __launch_bounds__(GemmEpi<BN, kStages>::kThreads, (kStages > 4) ? 1 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using S = GemmSmem<BN, kStages>;
@@ -111,9 +123,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
                     p.tiles_per_batch > 0 ? batch : 0);
         tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
+#ifndef F5_EPI_PROBE
         if (kb == 0) ts_mark(p, cta_lin, 3);
+#endif
       }
+#ifndef F5_EPI_PROBE
       ts_mark(p, cta_lin, 4);
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -143,7 +159,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else {
     // ===================== epilogue =====================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
+    using E = GemmEpi<BN, kStages>;
+    constexpr int BNG = E::kCols;
+    const int grp = (warp - 2) >> 2;       // 0: columns [0, BNG), 1: [BNG, BN)
+    const int lg = warp & 3;               // TMEM lane group this warp may access
+    const int et = ((warp - 2) & 3) * 32 + lane;
+    const int n0g = n0 + grp * BNG;
     const int r_in_tile = lg * 32 + lane;
     const int m_in_batch = m_in_batch0 + r_in_tile;
     const int row = row0 + r_in_tile;
@@ -164,20 +185,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
 
     // operand staging, overlapped with the main loop
-    float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset);
-    float* gate_s = bias_s + BN;
-    epi_stage_cols<BN>(p, n0, (warp - 2) * 32 + lane, bias_s, gate_s);
+    float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + grp * BNG;
+    float* gate_s = reinterpret_cast<float*>(smem + S::kColsOffset) + BN + grp * BNG;
+    epi_stage_cols<BNG>(p, n0g, et, bias_s, gate_s);
     float2 cs[ROPE ? 32 : 1];
     epi_load_rope<ROPE>(p, pos, cs);
     constexpr bool kPreloadAll = (kStages > 4);   // single-wave variant: one CTA per SM
-    float4 res_all[kPreloadAll ? BN / 32 : 1][8];
+    float4 res_all[kPreloadAll ? BNG / 32 : 1][8];
     if (kPreloadAll) {
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) epi_load_resid(p, row, n0 + c * 32, row_ok, res_all[c]);
+      for (int c = 0; c < BNG / 32; ++c) epi_load_resid(p, row, n0g + c * 32, row_ok, res_all[c]);
     } else {
-      epi_load_resid(p, row, n0, row_ok, res_all[0]);
+      epi_load_resid(p, row, n0g, row_ok, res_all[0]);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // bias_s / gate_s visible to the 4 epilogue warps
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // bias_s / gate_s visible to the group
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -187,24 +208,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     pdl_launch_dependents();
     if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 7);
     {
-      // all MMAs have retired (tmem_full), so the operand ring is idle: its first 32 KB stage the stores
+      // all MMAs have retired (tmem_full), so the operand ring is idle: its first 32 KB per group stage the stores
       EpiStage stg;
-      stg.buf = smem;
-      stg.et = (warp - 2) * 32 + lane;
+      stg.buf = smem + grp * 32768;
+      stg.et = et;
       stg.r = r_in_tile;
       stg.row0 = row0;
       stg.rows_valid = p.tiles_per_batch > 0 ? min(128, p.rows_per_batch - m_in_batch0) : min(128, p.M - row0);
+      stg.bar_id = 1 + grp;
+      stg.probe_cta = cta_lin;
+      const uint32_t tacc = tmem_base + grp * BNG + ((uint32_t)(lg * 32) << 16);
       if constexpr (kPreloadAll) {
-        epi_drain_tile_preloaded<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s,
-                                                          gate_s, cs, res_all, p, n0, row, b_idx, row_ok,
-                                                          row_valid, stg);
+        epi_drain_tile_preloaded<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all, p, n0g, row, b_idx,
+                                                           row_ok, row_valid, stg);
       } else {
-        epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + ((uint32_t)(lg * 32) << 16), bias_s, gate_s, cs,
-                                                res_all[0], p, n0, row, b_idx, row_ok, row_valid, stg);
+        epi_drain_tile<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all[0], p, n0g, row, b_idx, row_ok,
+                                                 row_valid, stg);
       }
     }
     tc_fence_before();
-    if (warp == 2 && lane == 0) ts_mark(p, cta_lin, 8);
+    if (warp == 2 + 4 * (GemmEpi<BN, kStages>::kGroups - 1) && lane == 0) ts_mark(p, cta_lin, 8);
   }
 
   __syncthreads();
