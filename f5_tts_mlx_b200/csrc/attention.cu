@@ -34,6 +34,7 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   p.ldo = (int)ld_out;
   p.handoff = 1;
   static bool attr_set = false;
+  static int poly = 0;      // pairs per 8 exponentials moved to the FMA pipe (F5_ATTN_POLY=0|1|2)
   static int handoff = 2;   // 0 off, 1 strict alternation of the exponential loops, 2 release at half time
   static int variant = 4;   // 2: two query tiles per CTA, O in TMEM (attention2_sm100.cuh); 1: v1
   if (!attr_set) {
@@ -43,6 +44,12 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
                                        Attn2Smem::kTotal));
     F5_CHECK_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Attn2Smem::kTotal));
+    F5_CHECK_CUDA((cudaFuncSetAttribute(attn2_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Attn2Smem::kTotal)));
+    F5_CHECK_CUDA((cudaFuncSetAttribute(attn2_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Attn2Smem::kTotal)));
+    const char* po = getenv("F5_ATTN_POLY");
+    if (po) poly = atoi(po);
     F5_CHECK_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Attn3Smem::kTotal));
     const char* v = getenv("F5_ATTN_VARIANT");
@@ -69,7 +76,13 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
     dim3 grid2(cdiv(frames, 256), heads, batch);
     ProfScope ps2(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
                   2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
-    if (variant == 4)
+    if (variant == 4 && poly == 1)
+      F5_CHECK_CUDA((launch_kernel(attn2_fwd_kernel<true, 1>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
+                                   reinterpret_cast<cudaStream_t>(stream_), tm, p)));
+    else if (variant == 4 && poly == 2)
+      F5_CHECK_CUDA((launch_kernel(attn2_fwd_kernel<true, 2>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
+                                   reinterpret_cast<cudaStream_t>(stream_), tm, p)));
+    else if (variant == 4)
       F5_CHECK_CUDA(launch_kernel(attn2_fwd_kernel<true>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
                                   reinterpret_cast<cudaStream_t>(stream_), tm, p));
     else

@@ -55,7 +55,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 // memory) instead of a swizzled smem tile.  Timeline probes (r01) showed the SS variant bound by shared-memory
 // bandwidth: per key tile the two groups moved 256 KB through smem (K/V fill 32, S operands 64, PV operands
 // 96, P stores 64) = 2048 clk at 128 B/clk, on top of the 2048 clk MUFU floor; with P in TMEM it is 128 KB.
-template <bool kPT>
+// kPoly: pairs per chunk of 8 exponentials evaluated on the FMA/ALU pipes (ex2_poly2) instead of MUFU.
+template <bool kPT, int kPoly = 0>
 __global__ void __launch_bounds__(384, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -292,7 +293,14 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         for (int c = 0; c < 16; ++c) {   // 16 chunks of 8 probabilities = 16 bytes
           float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), kLog2e, -mb));
+          for (int i = 0; i < 8 - 2 * kPoly; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[c * 8 + i]), kLog2e, -mb));
+#pragma unroll
+          for (int i = 8 - 2 * kPoly; i < 8; i += 2) {
+            const float2 pp = ex2_poly2(make_float2(fmaf(__uint_as_float(sv[c * 8 + i]), kLog2e, -mb),
+                                                    fmaf(__uint_as_float(sv[c * 8 + i + 1]), kLog2e, -mb)));
+            e[i] = pp.x;
+            e[i + 1] = pp.y;
+          }
           l0 += e[0] + e[4]; l1 += e[1] + e[5]; l2 += e[2] + e[6]; l3 += e[3] + e[7];
           if (c == 7 && p.handoff == 2 && handoff) {   // early release: the other group may start at half time
             if (g == 0) asm volatile("bar.arrive 3, 256;\n" ::: "memory");

@@ -31,13 +31,22 @@ ln_mod_kernel(const float* __restrict__ x, void* __restrict__ y, int rows,
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * D);
-  float4 v[IT];
+  // the modulation vectors do not depend on x: request them together with the row, so that their L2 round
+  // trip overlaps the row's instead of following the two reductions
+  const int b_idx = rows_per_batch > 0 ? warp / rows_per_batch : 0;
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b_idx * mod_batch_stride);
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b_idx * mod_batch_stride);
+  float4 v[IT], g[IT], h[IT];
   float s = 0.f;
 #pragma unroll
+  for (int i = 0; i < IT; ++i) v[i] = xr[i * 32 + lane];
+#pragma unroll
   for (int i = 0; i < IT; ++i) {
-    v[i] = xr[i * 32 + lane];
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
+    g[i] = sc[i * 32 + lane];
+    h[i] = sh[i * 32 + lane];
   }
+#pragma unroll
+  for (int i = 0; i < IT; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.f / D);
   float q = 0.f;
 #pragma unroll
@@ -46,18 +55,13 @@ ln_mod_kernel(const float* __restrict__ x, void* __restrict__ y, int rows,
     q += a * a + b * b + c * c + d * d;
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-6f);
-  const int b_idx = rows_per_batch > 0 ? warp / rows_per_batch : 0;
-  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b_idx * mod_batch_stride);
-  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b_idx * mod_batch_stride);
   const float one = add_one ? 1.f : 0.f;
 #pragma unroll
   for (int i = 0; i < IT; ++i) {
-    const float4 g = sc[i * 32 + lane];
-    const float4 h = sh[i * 32 + lane];
-    float a = (v[i].x - mean) * rstd * (one + g.x) + h.x;
-    float b = (v[i].y - mean) * rstd * (one + g.y) + h.y;
-    float c = (v[i].z - mean) * rstd * (one + g.z) + h.z;
-    float d = (v[i].w - mean) * rstd * (one + g.w) + h.w;
+    float a = (v[i].x - mean) * rstd * (one + g[i].x) + h[i].x;
+    float b = (v[i].y - mean) * rstd * (one + g[i].y) + h[i].y;
+    float c = (v[i].z - mean) * rstd * (one + g[i].z) + h[i].z;
+    float d = (v[i].w - mean) * rstd * (one + g[i].w) + h[i].w;
     if (OUT_F32)
       reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)warp * D)[i * 32 + lane] =
           make_float4(a, b, c, d);
