@@ -58,7 +58,7 @@ class GemmArgs(C.Structure):
         ("q_scale", C.c_float), ("q_cols", C.c_int32),
         ("tile_n", C.c_int32),
         ("out2_bf16", C.c_void_p), ("ldo2", C.c_int64),
-        ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("variant", C.c_int32), ("w_static", C.c_int32),
         ("debug_ts", C.c_void_p),
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
     ]

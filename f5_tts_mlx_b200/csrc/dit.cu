@@ -27,6 +27,7 @@ static f5_gemm_args gemm_base(const void* a, int64_t lda, const void* w, int64_t
   g.conv_taps = 1;
   g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16 ? 1 : 0;
   g.q_scale = 1.f;
+  g.w_static = 1;   // every W on this path is a model weight
   return g;
 }
 

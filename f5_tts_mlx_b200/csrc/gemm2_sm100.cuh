@@ -144,6 +144,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 1);
+  // first ring of B (weight) tiles of this cluster's first tile: requested before the PDL wait (gemm_sm100.cuh)
+  const int early_b = (p.w_static && cluster_id < total_tiles) ? min(kStages, num_kb) : 0;
+  if (warp == 0 && lane == 0) {
+    const int n0e = (cluster_id % n_tiles) * BN;
+    for (int kb = 0; kb < early_b; ++kb) {
+      if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * S::kStageBytes);
+      tma_load_2d_2sm(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * 64,
+                      n0e + (int)rank * (BN / 2));
+    }
+  }
   pdl_wait();
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 2);
 
@@ -172,12 +182,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          const bool early = kcount < early_b;   // B tile and expect_tx already issued before the PDL wait
+          if (rank == 0 && !early) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
           const int tap = kb / kb_per_tap;
           const int kc = kb - tap * kb_per_tap;
           const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
           tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
-          tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * 64, n0 + (int)rank * (BN / 2));
+          if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * 64, n0 + (int)rank * (BN / 2));
           if (kcount == 0) ts_mark(p, blockIdx.x, 3);
         }
       }

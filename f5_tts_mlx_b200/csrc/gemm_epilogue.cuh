@@ -34,6 +34,7 @@ struct GemmParams {
   __nv_bfloat16* out2;     // optional bf16 copy of the result
   int ldo2;
   unsigned long long* ts;  // debug: per-CTA phase timestamps (globaltimer ns), 10 slots per CTA, or null
+  int w_static;            // B operand may be fetched before the PDL wait (weights)
   const char* pf_ptr;      // weights of a LATER GEMM to pull into L2 while this one runs, or null
   long long pf_bytes;
 };

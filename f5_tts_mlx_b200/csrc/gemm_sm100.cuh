@@ -104,6 +104,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) ts_mark(p, cta_lin, 1);
+  // weights do not depend on the predecessor kernel: the first ring of B tiles is requested BEFORE the PDL
+  // wait, so their (possibly HBM) latency runs under the predecessor's tail
+  const int early_b = p.w_static ? min(kStages, num_kb) : 0;
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < early_b; ++kb) {
+      mbar_expect_tx(&full_bar[kb], S::kStageBytes);
+      tma_load_2d(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * 64, n0);
+    }
+  }
   pdl_wait();   // predecessor's outputs (our A operand / residual) are complete and visible
   if (threadIdx.x == 0) ts_mark(p, cta_lin, 2);
 
@@ -116,13 +125,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * S::kStageBytes;
         uint8_t* sb = sa + S::kABytes;
-        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        if (kb >= early_b) mbar_expect_tx(&full_bar[s], S::kStageBytes);
         const int tap = kb / kb_per_tap;
         const int kc = kb - tap * kb_per_tap;
         const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
         tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
                     p.tiles_per_batch > 0 ? batch : 0);
-        tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
+        if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
 #ifndef F5_EPI_PROBE
         if (kb == 0) ts_mark(p, cta_lin, 3);
 #endif

@@ -95,7 +95,9 @@ typedef struct f5_gemm_args {
   void* out2_bf16;        /* optional second copy of the result as bf16 [rows, ldo2], or NULL    */
   int64_t ldo2;
   int32_t variant;        /* 0 auto | 1 single-CTA 128xBN tiles | 2 persistent CTA-pair 256xBN    */
-  int32_t reserved;
+  int32_t w_static;       /* nonzero: `w` is never written by work that precedes this call on the stream
+                             (model weights): the kernel may start fetching it before its programmatic
+                             dependency on the preceding kernel has resolved                           */
   void* debug_ts;         /* NULL, or uint64 [ctas, 10]: per-CTA phase timestamps (globaltimer ns)  */
   const void* prefetch;   /* NULL, or device memory (weights of a later GEMM) to pull into L2       */
   int64_t prefetch_bytes;
