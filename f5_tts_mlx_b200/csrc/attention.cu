@@ -33,68 +33,36 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ld_out;
   p.handoff = 1;
-  static bool attr_set = false;
-  static int poly = 0;      // pairs per 8 exponentials moved to the FMA pipe (F5_ATTN_POLY=0|1|2)
-  static int handoff = 2;   // 0 off, 1 strict alternation of the exponential loops, 2 release at half time
-  static int variant = 4;   // 2: two query tiles per CTA, O in TMEM (attention2_sm100.cuh); 1: v1
-  if (!attr_set) {
-    F5_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnSmem::kTotal));
-    F5_CHECK_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Attn2Smem::kTotal));
-    F5_CHECK_CUDA(cudaFuncSetAttribute(attn2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Attn2Smem::kTotal));
-    F5_CHECK_CUDA((cudaFuncSetAttribute(attn2_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Attn2Smem::kTotal)));
-    F5_CHECK_CUDA((cudaFuncSetAttribute(attn2_fwd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Attn2Smem::kTotal)));
-    const char* po = getenv("F5_ATTN_POLY");
-    if (po) poly = atoi(po);
-    F5_CHECK_CUDA(cudaFuncSetAttribute(attn3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Attn3Smem::kTotal));
+  // F5_ATTN_VARIANT: 4 (default) two query tiles per CTA, S/P/O in TMEM; 2 same with P in shared memory;
+  // 3 sixteen softmax warps (experimental); 1 first version.  F5_ATTN_HANDOFF: 2 (default) a softmax group is
+  // released when the other is half way through its exponentials, 1 strict alternation, 0 off.
+  // F5_ATTN_POLY: pairs per 8 exponentials evaluated on the FMA pipe (0 default; 1, 2 measured no faster).
+  static int variant = -1, handoff = 2, poly = 0;
+  if (variant < 0) {
     const char* v = getenv("F5_ATTN_VARIANT");
-    if (v && v[0] == '1') variant = 1;
-    if (v && v[0] == '2') variant = 2;
-    if (v && v[0] == '3') variant = 3;
-    if (v && v[0] == '4') variant = 4;
     const char* ho = getenv("F5_ATTN_HANDOFF");
-    if (ho && ho[0] == '0') handoff = 0;
-    if (ho && ho[0] == '1') handoff = 1;
-    attr_set = true;
+    const char* po = getenv("F5_ATTN_POLY");
+    if (ho && ho[0] >= '0' && ho[0] <= '2') handoff = ho[0] - '0';
+    if (po && po[0] >= '0' && po[0] <= '2') poly = po[0] - '0';
+    variant = (v && v[0] >= '1' && v[0] <= '4') ? v[0] - '0' : 4;
   }
   p.handoff = handoff;
   p.ts = g_attn_ts;
-  if (variant == 3) {
-    dim3 grid3(cdiv(frames, 256), heads, batch);
-    ProfScope ps3(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
-                  2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
-    F5_CHECK_CUDA(launch_kernel(attn3_fwd_kernel, grid3, dim3(640), Attn3Smem::kTotal,
-                                reinterpret_cast<cudaStream_t>(stream_), tm, p));
-    return 0;
-  }
-  if (variant == 2 || variant == 4) {
-    dim3 grid2(cdiv(frames, 256), heads, batch);
-    ProfScope ps2(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
-                  2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
-    if (variant == 4 && poly == 1)
-      F5_CHECK_CUDA((launch_kernel(attn2_fwd_kernel<true, 1>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
-                                   reinterpret_cast<cudaStream_t>(stream_), tm, p)));
-    else if (variant == 4 && poly == 2)
-      F5_CHECK_CUDA((launch_kernel(attn2_fwd_kernel<true, 2>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
-                                   reinterpret_cast<cudaStream_t>(stream_), tm, p)));
-    else if (variant == 4)
-      F5_CHECK_CUDA(launch_kernel(attn2_fwd_kernel<true>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
-                                  reinterpret_cast<cudaStream_t>(stream_), tm, p));
-    else
-      F5_CHECK_CUDA(launch_kernel(attn2_fwd_kernel<false>, dim3(grid2), dim3(384), Attn2Smem::kTotal,
-                                  reinterpret_cast<cudaStream_t>(stream_), tm, p));
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
+               2.0 * batch * (double)frames * heads * 64.0 * 4.0, stream);
+  auto launch = [&](auto kern, SmemAttrOnce& once, dim3 grid, int threads, int smem) -> int {
+    F5_CHECK_CUDA(ensure_dyn_smem(once, kern, smem));
+    F5_CHECK_CUDA(launch_kernel(kern, grid, dim3(threads), smem, stream, tm, p));
     F5_CHECK_CUDA(cudaGetLastError());
     return 0;
-  }
-  dim3 grid(cdiv(frames, 128), heads, batch);
-  ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
-               2.0 * batch * (double)frames * heads * 64.0 * 4.0, reinterpret_cast<cudaStream_t>(stream_));
-  F5_CHECK_CUDA(launch_kernel(attn_fwd_kernel, dim3(grid), dim3(192), AttnSmem::kTotal, reinterpret_cast<cudaStream_t>(stream_), tm, p));
-  F5_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  };
+  const dim3 grid256(cdiv(frames, 256), heads, batch);
+  static SmemAttrOnce o1, o2, o3, o4, o41, o42;
+  if (variant == 3) return launch(attn3_fwd_kernel, o3, grid256, 640, Attn3Smem::kTotal);
+  if (variant == 2) return launch(attn2_fwd_kernel<false, 0>, o2, grid256, 384, Attn2Smem::kTotal);
+  if (variant == 4 && poly == 1) return launch(attn2_fwd_kernel<true, 1>, o41, grid256, 384, Attn2Smem::kTotal);
+  if (variant == 4 && poly == 2) return launch(attn2_fwd_kernel<true, 2>, o42, grid256, 384, Attn2Smem::kTotal);
+  if (variant == 4) return launch(attn2_fwd_kernel<true, 0>, o4, grid256, 384, Attn2Smem::kTotal);
+  return launch(attn_fwd_kernel, o1, dim3(cdiv(frames, 128), heads, batch), 192, AttnSmem::kTotal);
 }

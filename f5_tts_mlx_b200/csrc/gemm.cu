@@ -12,12 +12,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                        dim3 grid, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages>;
   auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    F5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       S::kTotal));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;  // per instantiation
+  F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
   const double taps = p.conv_taps;
   ProfScope ps(PROF_GEMM, 2.0 * p.M * (double)p.N * (double)p.k_per_tap * taps,
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
@@ -51,12 +47,8 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
                         int n_tiles, int total_tiles, cudaStream_t stream) {
   using S = Gemm2Smem<BN, kStages>;
   auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    F5_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       S::kTotal));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;
+  F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
   static int num_pairs = 0;
   if (num_pairs == 0) {
     int dev = 0, sms = 0;

@@ -54,6 +54,22 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember it per (kernel instantiation,
+// device) so that one process driving several GPUs does not launch with the default 48 KB limit on the second.
+struct SmemAttrOnce {
+  unsigned long long done = 0;   // bit d: set on device d
+};
+template <typename K>
+inline cudaError_t ensure_dyn_smem(SmemAttrOnce& once, K kern, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((once.done >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) once.done |= 1ull << dev;
+  return e;
+}
+
 // ---- launch accounting + optional per-kernel-family device timing (bench.py roofline) ----
 // Every launcher opens a ProfScope around its kernel launch.  The launch counter is always on;
 // when profiling is enabled (f5_prof_enable) a CUDA event pair brackets the launch on its stream
