@@ -238,6 +238,11 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     from f5_tts_mlx_b200.vocos import Vocos
     from f5_tts_mlx_b200.weights import VocosConfig, random_dit_weights, random_vocos_weights
 
+    if not torch.cuda.is_available():
+        # the product path has no CPU fallback: say so instead of measuring something else
+        sys.stderr.write("bench.py: no CUDA device visible; this arm runs libf5b200.so on a B200 only "
+                         "(the CPU baseline is `--impl reference`)\n")
+        raise SystemExit(3)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()

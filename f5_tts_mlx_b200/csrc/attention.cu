@@ -3,7 +3,6 @@
 
 #include "attention_sm100.cuh"
 #include "attention2_sm100.cuh"
-#include "attention3_sm100.cuh"
 #include "host_common.h"
 
 static unsigned long long* g_attn_ts = nullptr;
@@ -34,7 +33,7 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   p.ldo = (int)ld_out;
   p.handoff = 1;
   // F5_ATTN_VARIANT: 4 (default) two query tiles per CTA, S/P/O in TMEM; 2 same with P in shared memory;
-  // 3 sixteen softmax warps (experimental); 1 first version.  F5_ATTN_HANDOFF: 2 (default) a softmax group is
+  // 1 first version.  F5_ATTN_HANDOFF: 2 (default) a softmax group is
   // released when the other is half way through its exponentials, 1 strict alternation, 0 off.
   // F5_ATTN_POLY: pairs per 8 exponentials evaluated on the FMA pipe (0 default; 1, 2 measured no faster).
   static int variant = -1, handoff = 2, poly = 0;
@@ -44,7 +43,7 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
     const char* po = getenv("F5_ATTN_POLY");
     if (ho && ho[0] >= '0' && ho[0] <= '2') handoff = ho[0] - '0';
     if (po && po[0] >= '0' && po[0] <= '2') poly = po[0] - '0';
-    variant = (v && v[0] >= '1' && v[0] <= '4') ? v[0] - '0' : 4;
+    variant = (v && (v[0] == '1' || v[0] == '2' || v[0] == '4')) ? v[0] - '0' : 4;
   }
   p.handoff = handoff;
   p.ts = g_attn_ts;
@@ -58,8 +57,7 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
     return 0;
   };
   const dim3 grid256(cdiv(frames, 256), heads, batch);
-  static SmemAttrOnce o1, o2, o3, o4, o41, o42;
-  if (variant == 3) return launch(attn3_fwd_kernel, o3, grid256, 640, Attn3Smem::kTotal);
+  static SmemAttrOnce o1, o2, o4, o41, o42;
   if (variant == 2) return launch(attn2_fwd_kernel<false, 0>, o2, grid256, 384, Attn2Smem::kTotal);
   if (variant == 4 && poly == 1) return launch(attn2_fwd_kernel<true, 1>, o41, grid256, 384, Attn2Smem::kTotal);
   if (variant == 4 && poly == 2) return launch(attn2_fwd_kernel<true, 2>, o42, grid256, 384, Attn2Smem::kTotal);
