@@ -265,6 +265,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     cond_d, y0_d = cond.to(dev), y0.to(dev)
     kw = dict(steps=args.ode_steps, method=args.method, cfg_strength=args.cfg, sway_sampling_coef=-1.0,
               return_trajectory=False)
+    if N > 4096:
+        kw["max_duration"] = N        # long-form (config 5): the reference's default clip is 4096 frames (cfm.py:277)
 
     def barrier():
         if world > 1:
@@ -389,7 +391,8 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                     "ms_per_step": 1e3 * te.item() / e2e_steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "roofline": roof, "cpu_baseline": cpu,
-            "rtf": (ms_total / args.steps / 1e3) / ((N - NR) * HOP / SR)}
+            "rtf": (ms_total / args.steps / 1e3) / ((N - NR) * HOP / SR),
+            "generated_frames_per_s": value * (N - NR) / N}
     print(json.dumps(line), flush=True)
 
 
