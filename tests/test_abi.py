@@ -79,3 +79,26 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not pat.search(src), f"{fn} imports the oracle"
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """include/f5_b200.h compiles as strict C99 and a C program links against libf5b200.so: the boundary has no
+    C++ or torch types.  The consumer also checks that the C compiler's struct layout equals the library's."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    _lib.load()                                            # builds the library if needed
+    pkg = os.path.join(ROOT, "f5_tts_mlx_b200")
+    exe = str(tmp_path / "consumer")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi", "consumer.c"), "-o", exe, "-L", pkg, "-l:libf5b200.so",
+           f"-Wl,-rpath,{pkg}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi=" in r.stdout and "structs=10" in r.stdout
+    if not torch.cuda.is_available():
+        assert "device_check=-3" in r.stdout and "gemm_rc=-3" in r.stdout     # F5_ERR_NO_DEVICE, no CPU fallback
