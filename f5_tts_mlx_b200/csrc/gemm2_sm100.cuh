@@ -5,15 +5,19 @@
 // `tcgen05.mma.cta_group::2` stream issued by the leader CTA: CTA r holds rows [128r, 128r+128) of
 // A and HALF of the B tile (BN/2 weight rows) in its shared memory, the tensor cores of both SMs
 // read both halves, and each CTA's TMEM receives its 128 accumulator rows.  Per k-block a CTA
-// pulls 16 KB (A) + BN/2*128 B (B) through L2 for 128 x BN x 64 MACs — twice the arithmetic
-// intensity of the single-CTA 128 x 128 tile, which is what lifts the L2->SM bandwidth cap.
+// pulls 16 KB (A) + BN/2*128 B (B) into shared memory for 128 x BN x 64 MACs — twice the arithmetic
+// intensity of the single-CTA 128 x 128 tile.  That is what matters: shared memory moves 128 B/clk per SM and
+// carries both the TMA fill and the tensor core's operand reads (tools/microbench/); at BN = 256 the pair tile
+// needs exactly that, the single-CTA tile twice as much.
 //
-// Persistent: grid = min(74 clusters, tiles); tiles are walked n-fastest.  Warp roles (256 threads):
-//   warp 0  TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
+// Persistent: grid = min(74 clusters, tiles); tiles are walked n-fastest.  Warp roles (384 threads):
+//   warp 0  TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier); the first
+//           ring of weight tiles is requested before the PDL wait when the caller marks W as static
 //   warp 1  MMA issuer (leader only); tcgen05.commit multicast frees the stage in both CTAs
-//   warp 2  TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-7 epilogue (both CTAs): drains accumulator stage i while the MMAs fill stage i^1,
-//           then arrives on the leader's tmem_empty barrier
+//   warp 2  TMEM allocator (2 accumulator stages x BN columns), warp 3 L2 prefetch of the next GEMM's weights
+//   warps 4-7, 8-11  two epilogue groups (both CTAs) interleaving the tile's 64-column units: they drain
+//           accumulator stage i while the MMAs fill stage i^1, then arrive on the leader's tmem_empty barrier;
+//           setmaxnreg hands registers from warps 0-3 (40) to the epilogue warps (232)
 #pragma once
 #include "gemm_epilogue.cuh"
 

@@ -1,12 +1,14 @@
 // tcgen05 + TMA GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] (bf16, K-major) · W[N,K]^T (bf16) )
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0     TMA producer   (one elected lane): A/B k-blocks -> 128B-swizzled smem ring
+// One CTA computes one 128 x BN output tile.  Warp roles (192 or 320 threads):
+//   warp 0     TMA producer   (one elected lane): A/B k-blocks -> 128B-swizzled smem ring; the first ring of
+//              weight tiles is requested before the PDL wait when the caller marks W as static
 //   warp 1     MMA issuer     (one elected lane): tcgen05.mma kind::f16, fp32 accumulator in TMEM
 //   warps 2-5  epilogue       (128 threads = 128 TMEM lanes = 128 output rows)
+//   warps 6-9  second epilogue group (one-CTA-per-SM instantiation only, see GemmEpi)
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA) and one tmem_full mbarrier (MMA -> epilogue).
-// With kStages*(16+BN/8) KB of smem two CTAs can be co-resident per SM, so one CTA's epilogue
-// overlaps the other's main loop (TMEM: 2 x BN columns <= 512).
+// With kStages <= 4 (kStages*(16+BN/8) KB of smem) two CTAs are co-resident per SM, so one CTA's epilogue
+// overlaps the other's main loop (TMEM: 2 x BN columns <= 512); kStages = 6 is the one-wave variant.
 //
 // The same kernel runs the 1-D convolutions of the path as implicit GEMMs: the A operand is a
 // 3-D tensor map (channels, frames, batch) and k-block kb reads the tile shifted by
