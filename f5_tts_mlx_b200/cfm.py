@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Callable, Dict, List, Literal, Optional, Tuple
+from typing import Callable, Dict, Literal, Optional, Tuple
 
 import torch
 import torch.nn.functional as F

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .weights import DiTConfig, DitWeightsC, PackedDiT, Weights
+from .weights import DiTConfig, PackedDiT, Weights
 
 
 class DitBuffersC(C.Structure):

@@ -11,7 +11,7 @@ all-reduce(MAX) of an integer; equal-length batches (all BASELINE configs) never
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

@@ -10,13 +10,12 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional
+from dataclasses import dataclass
+from typing import Dict, Optional
 
 import numpy as np
 import torch
 
-from . import _lib
 
 Weights = Dict[str, torch.Tensor]
 

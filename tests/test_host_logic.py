@@ -1,6 +1,5 @@
 """Host-side logic of the package (no GPU): helpers mirror the reference's utils, the solver
 evaluation-time schedule, weight packing, key conversion, sharding."""
-import os
 
 import numpy as np
 import pytest
