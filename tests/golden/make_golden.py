@@ -88,3 +88,34 @@ sec = O.duration_predictor(mel, text, dWo, O.DurationConfig(), lens=lens)
 np.savez_compressed(os.path.join(HERE, "duration_small.npz"), mel=mel.numpy(), text=text.numpy(), lens=lens.numpy(),
                     seconds=sec.numpy(), weight_seed=777)
 print("duration", sec)
+
+# (g) per-operator input/output pairs on a small DiT (dim 128, 2 heads, 1 block)
+from f5_tts_mlx_b200.weights import DiTConfig as PkgDiTConfig                     # noqa: E402
+tiny = PkgDiTConfig(dim=128, depth=1, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_num_embeds=50)
+tcfg = O.DiTConfig(dim=128, depth=1, heads=2, ff_mult=2, text_num_embeds=50, text_dim=64, conv_layers=1)
+Wt = random_dit_weights(tiny, seed=77)
+g = torch.Generator().manual_seed(5)
+B, N = 2, 40
+x = torch.randn(B, N, 128, generator=g)
+t_emb = O.timestep_embedding(torch.tensor([0.25, 0.9]), Wt)
+mask = torch.arange(N)[None, :] < torch.tensor([40, 23])[:, None]
+rope = O.rotary_freqs(N)
+text = torch.randint(0, 50, (B, 12), generator=g, dtype=torch.int32); text[1, 7:] = -1
+xt = torch.randn(B, N, 64, generator=g)
+pairs = dict(
+    x=x.numpy(), text=text.numpy(), xt=xt.numpy(), weight_seed=77,
+    time_embed=t_emb.numpy(),
+    grn=O.grn(torch.randn(B, N, 128, generator=torch.Generator().manual_seed(6)),
+              Wt["transformer.text_embed.text_blocks.layers.0.grn.gamma"],
+              Wt["transformer.text_embed.text_blocks.layers.0.grn.beta"]).numpy(),
+    convnext=O.convnext_v2_block(xt, Wt, "transformer.text_embed.text_blocks.layers.0.").numpy(),
+    text_embed=O.text_embedding(text, N, False, Wt, tcfg).numpy(),
+    text_embed_drop=O.text_embedding(text, N, True, Wt, tcfg).numpy(),
+    conv_pos=O.conv_position_embedding(x, Wt).numpy(),
+    attention=O.attention(x, mask, rope, Wt, "transformer.transformer_blocks.0.attn.", 2).numpy(),
+    attention_nomask=O.attention(x, None, rope, Wt, "transformer.transformer_blocks.0.attn.", 2).numpy(),
+    dit_block=O.dit_block(x, t_emb, mask, rope, Wt, 0, tcfg).numpy(),
+    rope_q=O.apply_rotary_pos_emb(x[:, None, :, :64], rope).numpy(),
+)
+np.savez_compressed(os.path.join(HERE, "ops_small.npz"), **pairs)
+print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))

@@ -234,3 +234,40 @@ def test_duration_predictor_golden_and_structure(golden_dir):
     ref = torch.nn.functional.rms_norm(x, (512,), W["duration.transformer.norm_out.weight"], eps=1e-5)
     got = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * W["duration.transformer.norm_out.weight"]
     assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_per_operator_known_answers(golden_dir):
+    """per-operator input/output pairs (tiny DiT: dim 128, 2 heads, 1 block), generated by
+    tests/golden/make_golden.py section (g).  Pins every building block of the oracle separately, so a regression is
+    localised to the operator, not just visible in the end-to-end fixtures."""
+    from f5_tts_mlx_b200.weights import DiTConfig as PkgDiTConfig
+    z = np.load(os.path.join(golden_dir, "ops_small.npz"))
+    tiny = PkgDiTConfig(dim=128, depth=1, heads=2, ff_mult=2, text_dim=64, conv_layers=1, text_num_embeds=50)
+    tcfg = ocfg_of(tiny)
+    W = random_dit_weights(tiny, seed=int(z["weight_seed"]))
+    x, text, xt = torch.from_numpy(z["x"]), torch.from_numpy(z["text"]), torch.from_numpy(z["xt"])
+    B, N, _ = x.shape
+    mask = torch.arange(N)[None, :] < torch.tensor([40, 23])[:, None]
+    rope = O.rotary_freqs(N)
+    t_emb = O.timestep_embedding(torch.tensor([0.25, 0.9]), W)
+    blk = "transformer.text_embed.text_blocks.layers.0."
+    got = {
+        "time_embed": t_emb,
+        "grn": O.grn(torch.randn(B, N, 128, generator=torch.Generator().manual_seed(6)), W[blk + "grn.gamma"],
+                     W[blk + "grn.beta"]),
+        "convnext": O.convnext_v2_block(xt, W, blk),
+        "text_embed": O.text_embedding(text, N, False, W, tcfg),
+        "text_embed_drop": O.text_embedding(text, N, True, W, tcfg),
+        "conv_pos": O.conv_position_embedding(x, W),
+        "attention": O.attention(x, mask, rope, W, "transformer.transformer_blocks.0.attn.", 2),
+        "attention_nomask": O.attention(x, None, rope, W, "transformer.transformer_blocks.0.attn.", 2),
+        "dit_block": O.dit_block(x, t_emb, mask, rope, W, 0, tcfg),
+        "rope_q": O.apply_rotary_pos_emb(x[:, None, :, :64], rope),
+    }
+    for k, v in got.items():
+        assert v.shape == z[k].shape, k
+        assert rel(v, torch.from_numpy(z[k])) < 2e-5, k
+    # structure the fixtures must show: padded text rows are zero; masking changes only what it should
+    assert (got["text_embed"][1, 7:] == 0).all() and (got["text_embed_drop"][1, 7:] == 0).all()
+    assert torch.equal(got["attention"][1, 23:], torch.zeros_like(got["attention"][1, 23:]))     # x * mask (dit.py:172-173)
+    assert rel(got["attention"][0], got["attention_nomask"][0]) < 1e-6                           # full-length row unaffected
