@@ -7,6 +7,15 @@ strip the reference samples from each waveform, concatenate, write a wav.  Devia
 the stdlib `wave` module (soundfile is not in the image); live playback (AudioPlayer, sounddevice)
 is out of scope, so `output_path=None` just returns the waveform; `duration=None` without
 `estimate_duration` needs a duration predictor exactly like the reference (ValueError otherwise).
+
+Pinned against the reference's own generate() executed through tests/mlx_shim
+(tests/golden/ref_generate_calls.json, tests/test_ref_pins.py): sentence split, text assembly,
+RMS normalisation, the single-generation path and every keyword that reaches `sample()` are identical.
+One deliberate difference, in the multi-sentence loop with `estimate_duration=True`: the reference
+estimates from the WHOLE text for every sentence and then re-scales its own previous result
+(`duration = int(duration * FRAMES_PER_SEC)` on the already-converted frame count, generate.py:206-209),
+so from the second sentence on the request grows by x93.75 per sentence and is clipped to
+max_duration = 4096 frames inside sample().  Here each sentence gets its own estimate.
 """
 from __future__ import annotations
 
@@ -148,7 +157,8 @@ def generate(
                                return_trajectory=False)
         waves.append(wave[audio.shape[0]:])                                       # strip the reference (generate.py:183)
     wave = torch.cat(waves, dim=0)
-    torch.cuda.synchronize()
+    if wave.is_cuda:
+        torch.cuda.synchronize()
     print(f"Generated {wave.shape[0] / SAMPLE_RATE:.2f}s of audio in {datetime.datetime.now() - start}.")
     if output_path is not None:
         write_wav(output_path, wave)
