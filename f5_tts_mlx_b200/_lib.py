@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libf5b200.so"
+import os as _os
+
+# F5_LIB: an alternative build of the SAME library (A/B measurements of kernel variants); default: the in-tree build
+_LIB_PATH = Path(_os.environ["F5_LIB"]) if _os.environ.get("F5_LIB") else Path(__file__).resolve().parent / "libf5b200.so"
 _lib = None
 
 
@@ -61,6 +64,8 @@ class GemmArgs(C.Structure):
         ("variant", C.c_int32), ("w_static", C.c_int32),
         ("debug_ts", C.c_void_p),
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
+        ("ln_scale", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_in_stats", C.c_void_p),
+        ("ln_tab", C.c_void_p), ("ln_tab_ld", C.c_int64),
     ]
 
 
@@ -73,6 +78,8 @@ SYMBOLS: dict[str, tuple] = {
     "f5_launch_count": (C.c_longlong, []),
     "f5_prof_enable": (C.c_int, [C.c_int]),
     "f5_prof_summary": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "f5_prof_graph_begin": (C.c_int, [C.c_void_p, C.c_int32]),
+    "f5_prof_graph_meta": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32]),
     "f5_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "f5_debug_gemm_ts": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32]),
     "f5_debug_attention_ts": (C.c_int, [C.c_void_p]),
@@ -86,6 +93,7 @@ SYMBOLS: dict[str, tuple] = {
                          C.c_int32, C.c_void_p]),
     "f5_dit_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_dit_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "f5_dit_ln_tab_ld": (C.c_int64, [C.c_void_p]),
     "f5_ode_eval_times": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_int32]),
     "f5_duration_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_mel_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -95,12 +95,12 @@ class _Plan:
     DiT session buffers, ODE state buffers and the captured CUDA graph of precompute + ODE loop."""
 
     def __init__(self, model: "F5TTS", batch: int, frames: int, text_cols: int, steps: int, method: str,
-                 sway: Optional[float], cfg_strength: float, masked: bool, keep_trajectory: bool):
+                 sway: Optional[float], cfg_strength: float, masked: bool, keep_trajectory: bool, bucketed: bool = False):
         tr = model.transformer
         self.t_grid = time_grid(steps, sway)
         self.tvals = ode_eval_times(self.t_grid, method)
         self.use_cfg = cfg_strength >= 1e-5
-        self.session: DitSession = tr.session(batch, frames, self.tvals.numel(), self.use_cfg, text_cols, masked)
+        self.session: DitSession = tr.session(batch, frames, self.tvals.numel(), self.use_cfg, text_cols, masked, bucketed)
         dev, d = tr.device, model.num_channels
         self.steps, self.method, self.cfg_strength = steps, method, float(cfg_strength)
         self.keep_trajectory = keep_trajectory
@@ -116,6 +116,7 @@ class _Plan:
 
     def run_eager(self, model: "F5TTS") -> None:
         tr = model.transformer
+        self.session.c.drop_flags = 0      # DiT.__call__ may have used this cached session with drop flags set
         tr.precompute(self.session)
         lib = _lib.load()
         tg = self.t_grid.numpy().ctypes.data_as(C.POINTER(C.c_float))
@@ -125,21 +126,26 @@ class _Plan:
             C.c_void_p(self.trajectory.data_ptr()) if self.trajectory is not None else None,
             C.c_void_p(self.scratch.data_ptr()) if self.scratch is not None else None, _stream()))
 
+    def capture(self, model: "F5TTS") -> None:
+        """Capture precompute + ODE loop into a CUDA graph (an eager pass must have run on this process before:
+        it sets per-kernel attributes and validates the arguments).  Leaves the state buffer unchanged."""
+        y0 = self.y.clone()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager(model)
+        self.graph = g
+        self.y.copy_(y0)
+
     def run(self, model: "F5TTS", use_graph: bool) -> None:
         if not use_graph:
             self.run_eager(model)
             return
         if self.graph is None:
-            # one eager pass first (sets per-kernel attributes, validates arguments), then capture
             y0 = self.y.clone()
             self.run_eager(model)
             torch.cuda.synchronize()
             self.y.copy_(y0)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.run_eager(model)
-            self.graph = g
-            self.y.copy_(y0)
+            self.capture(model)
         self.graph.replay()
 
 
@@ -169,7 +175,14 @@ class F5TTS:
         self._vocab_char_map = vocab_char_map
         self._vocoder = vocoder
         self._duration_predictor = duration_predictor
-        self._plans: Dict[tuple, _Plan] = {}
+        self._plans: Dict[tuple, _Plan] = {}      # LRU, most recently used last
+        self.plan_cache_size = 8
+        # Plan reuse across utterances of different length (generate()'s sentence loop): 0 = every distinct
+        # (frames, text columns) gets its own buffers + CUDA graph (the reference's exact shapes); k > 0 rounds the frame
+        # count up to a multiple of k and the text columns to a multiple of text_bucket, the real length travelling
+        # in a device-side scalar (f5_dit_buffers.valid_len) so one captured graph serves the whole bucket.
+        self.frame_bucket = 0
+        self.text_bucket = 32
         self.use_cuda_graph = True
         self.last_plan: Optional[_Plan] = None
 
@@ -187,14 +200,15 @@ class F5TTS:
         frame_rate = self._mel_spec.sample_rate // self._mel_spec.hop_length
         return (duration_in_sec * frame_rate / speed).to(torch.int32)
 
-    def _plan(self, batch, frames, text_cols, steps, method, sway, cfg_strength, masked, keep_traj) -> _Plan:
-        key = (batch, frames, text_cols, steps, method, sway, float(cfg_strength), masked, keep_traj)
-        p = self._plans.get(key)
+    def _plan(self, batch, frames, text_cols, steps, method, sway, cfg_strength, masked, keep_traj, bucketed=False) -> _Plan:
+        key = (batch, frames, text_cols, steps, method, sway, float(cfg_strength), masked, keep_traj, bucketed)
+        p = self._plans.pop(key, None)
         if p is None:
-            if len(self._plans) >= 2:
-                self._plans.pop(next(iter(self._plans)))
-            p = _Plan(self, batch, frames, text_cols, steps, method, sway, cfg_strength, masked, keep_traj)
-            self._plans[key] = p
+            while len(self._plans) >= max(1, self.plan_cache_size):
+                old = self._plans.pop(next(iter(self._plans)))
+                self.transformer.release_session(old.session)
+            p = _Plan(self, batch, frames, text_cols, steps, method, sway, cfg_strength, masked, keep_traj, bucketed)
+        self._plans[key] = p
         return p
 
     @torch.no_grad()
@@ -214,11 +228,16 @@ class F5TTS:
         max_duration=4096,
         y0: Optional[torch.Tensor] = None,
         return_trajectory: bool = True,
+        pad_frames: Optional[int] = None,
+        frame_bucket: Optional[int] = None,
     ) -> Tuple[torch.Tensor, torch.Tensor]:
         """cfm.py:264-402.  Extensions (default-compatible): `y0` injects the initial noise
         (b, n, mel) — MLX's RNG stream cannot be reproduced, so seeded parity is defined on injected
         noise; `return_trajectory=False` skips keeping all `steps` states (then `trajectory` is the
-        final state with a leading axis of 1)."""
+        final state with a leading axis of 1); `pad_frames` pads the batch to at least that many frames — a shard
+        of a ragged batch must use the GLOBAL maximum (parallel.global_frames) to reproduce the unsharded result,
+        because the reference's padding leaks into GRN and the ODE on padded frames; `frame_bucket` (default
+        self.frame_bucket) reuses one plan / CUDA graph for all lengths of a bucket, results unchanged."""
         dev = self.transformer.device
         if method not in METHODS:
             raise ValueError(f"Unknown method: {method}")
@@ -259,6 +278,8 @@ class F5TTS:
         duration = torch.maximum(lens + 1, duration)
         duration = torch.clip(duration, 0, max_duration)
         N = int(duration.max().item())
+        if pad_frames is not None:
+            N = max(N, int(pad_frames))
 
         # pad cond / cond_mask to N; step_cond (cfm.py:321-331)
         cond = F.pad(cond, (0, 0, 0, N - cond_seq_len)) if N >= cond_seq_len else cond[:, :N]
@@ -267,8 +288,17 @@ class F5TTS:
         masked = batch > 1                                            # cfm.py:333-336
         seq_len = duration.to(torch.int32).to(dev) if masked else None
 
-        plan = self._plan(batch, N, text.shape[1], steps, method, sway_sampling_coef, cfg_strength, masked,
-                          return_trajectory)
+        # frame / text bucketing: buffers and graph of the bucket, the real N in a device scalar
+        bucket = self.frame_bucket if frame_bucket is None else int(frame_bucket)
+        NB = N
+        if bucket > 0:
+            NB = -(-N // bucket) * bucket
+            tb = max(1, self.text_bucket)
+            tcols = -(-max(text.shape[1], 1) // tb) * tb
+            if tcols != text.shape[1]:
+                text = F.pad(text, (0, tcols - text.shape[1]), value=-1)
+        plan = self._plan(batch, NB, text.shape[1], steps, method, sway_sampling_coef, cfg_strength, masked,
+                          return_trajectory, bucket > 0)
         self.last_plan = plan
 
         # noise (cfm.py:369-375): same seed for every element, drawn as (mel, dur) then transposed
@@ -278,16 +308,23 @@ class F5TTS:
                 gen = torch.Generator().manual_seed(int(seed)) if exists(seed) else None
                 ys.append(torch.randn(self.num_channels, int(dur), generator=gen))
             y0 = pad_sequence(ys, padding_value=0).permute(0, 2, 1)
-        plan.session.set_inputs(text, step_cond, plan.tvals.to(dev), seq_len)
-        plan.y.copy_(y0.to(dev).float())
+        y0 = y0.to(dev).float()
+        if NB != N:
+            y0 = F.pad(y0, (0, 0, 0, NB - N))
+            step_cond_in = F.pad(step_cond, (0, 0, 0, NB - N))
+        else:
+            step_cond_in = step_cond
+        plan.session.set_inputs(text, step_cond_in, plan.tvals.to(dev), seq_len, frames_valid=N if bucket > 0 else None)
+        plan.y.copy_(y0)
 
         plan.run(self, self.use_cuda_graph)
 
+        # fresh tensors, like the reference: the plan's buffers are overwritten by the next call / graph replay
         if plan.trajectory is not None:
-            trajectory = plan.trajectory
+            trajectory = plan.trajectory[:, :, :N].clone()
             sampled = trajectory[-1]
         else:
-            sampled = plan.y
+            sampled = plan.y[:, :N].clone()
             trajectory = sampled[None]
         out = torch.where(cond_mask, cond, sampled)                  # cfm.py:395-397
         if exists(self._vocoder):

@@ -50,6 +50,7 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
                2.0 * batch * (double)frames * heads * 64.0 * 4.0, stream);
+  p.prof = ps.slot;
   auto launch = [&](auto kern, SmemAttrOnce& once, dim3 grid, int threads, int smem) -> int {
     F5_CHECK_CUDA(ensure_dyn_smem(once, kern, smem));
     F5_CHECK_CUDA(launch_kernel(kern, grid, dim3(threads), smem, stream, tm, p));

@@ -33,7 +33,8 @@ static f5_gemm_args gemm_base(const void* a, int64_t lda, const void* w, int64_t
 
 static int check_common(const f5_dit_weights* w, const f5_dit_buffers* b) {
   F5_REQUIRE(w && b, "dit: null weights/buffers");
-  F5_REQUIRE(w->dim % 128 == 0 && w->dim >= 256 && w->dim <= 2048, "dit: dim %d unsupported", w->dim);
+  F5_REQUIRE(w->dim % 128 == 0 && w->dim >= 256 && w->dim <= 1024,
+             "dit: dim %d unsupported (128 | dim, 256..1024: the grouped conv packs 16 groups of <= 64 channels)", w->dim);
   F5_REQUIRE(w->dim == w->heads * 64, "dit: dim %d != heads %d * 64", w->dim, w->heads);
   F5_REQUIRE(w->mel_dim % 4 == 0 && w->mel_dim <= 128, "dit: mel_dim %d", w->mel_dim);
   F5_REQUIRE(w->blocks && w->depth > 0, "dit: no blocks");
@@ -41,9 +42,21 @@ static int check_common(const f5_dit_weights* w, const f5_dit_buffers* b) {
   return 0;
 }
 
+static long long ln_tab_ld(const f5_dit_weights* w) {
+  return (long long)w->depth * (3 * w->dim + w->ff_inner) + 128;
+}
+// F5_LN_FUSED=0 keeps the separate LayerNorm+modulate launches even when the fused-AdaLN buffers are present
+static bool ln_fused(const f5_dit_buffers* b) {
+  static int env = -1;
+  if (env < 0) { const char* v = getenv("F5_LN_FUSED"); env = (v && v[0] == '0') ? 0 : 1; }
+  return env && b->ln_stats && b->ln_tab && b->ln_prep;
+}
+
 }  // namespace f5
 
 using namespace f5;
+
+extern "C" int64_t f5_dit_ln_tab_ld(const f5_dit_weights* w) { return w ? ln_tab_ld(w) : 0; }
 
 extern "C" int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* b, void* stream_) {
   if (int e = device_check()) return e;
@@ -85,6 +98,7 @@ extern "C" int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* 
   {
     f5_gemm_args g = gemm_base(b->ct_bf16, w->ct_ld, w->in_ct_w, w->ct_ld, R, D, w->ct_ld, b->hoist, D, false);
     g.bias = w->in_b;
+    if (b->valid_len) { g.rows_per_batch = N; g.num_batches = BU; g.row_len = b->valid_len; }   // bucket rows stay 0
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
 
@@ -98,6 +112,22 @@ extern "C" int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* 
     g.bias = w->mod_b;
     g.tile_n = 128;
     if (int e = f5_gemm_bf16(&g, st)) return e;
+  }
+  // ---- fused AdaLN: c1 = (1 + scale) W^T and c2 = shift W^T of every consuming Linear, for all times ----
+  if (ln_fused(b)) {
+    const int NM = w->depth * 6 * D + 2 * D, T = b->n_times, F = w->ff_inner;
+    const long long ld = ln_tab_ld(w);
+    if (int e = launch_ln_tab_prep(b->mod_table, b->ln_prep, T, w->depth, D, NM, st)) return e;
+    const __nv_bfloat16* prep = reinterpret_cast<const __nv_bfloat16*>(b->ln_prep);
+    for (int site = 0; site <= 2 * w->depth; ++site) {
+      const int l = site >> 1;
+      const void* wt; int n; long long off;
+      if (site == 2 * w->depth) { wt = w->proj_w; n = w->mel_dim; off = (long long)w->depth * (3 * D + F); }
+      else if (site & 1) { wt = w->blocks[l].ff1_w; n = F; off = (long long)l * (3 * D + F) + 3 * D; }
+      else { wt = w->blocks[l].qkv_w; n = 3 * D; off = (long long)l * (3 * D + F); }
+      f5_gemm_args g = gemm_base(prep + (size_t)site * 4 * T * D, D, wt, D, 4 * T, n, D, b->ln_tab + off, ld, false);
+      if (int e = f5_gemm_bf16(&g, st)) return e;
+    }
   }
   return 0;
 }
@@ -118,12 +148,17 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   static int pf_env = -1;
   if (pf_env < 0) { const char* v = getenv("F5_PREFETCH"); pf_env = (v && v[0] == '0') ? 0 : 1; }
   const bool prefetch = pf_env && R <= 16384;
+  const bool fused = ln_fused(b);
+  const long long tab_ld = ln_tab_ld(w);
+  const float* tab = fused ? b->ln_tab + (size_t)4 * ti * tab_ld : nullptr;   // this time's 4 operand rows
 
   // ---- InputEmbedding (dit.py:249-251): x·Wx + hoist, then + ConvPositionEmbedding ----
   {
     f5_gemm_args g = gemm_base(b->y_bf16, 128, w->in_x_w, 128, R, D, 128, b->h, D, false);
     g.resid = b->hoist; g.ldr = D;
     g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+    // bucket rows (>= valid_len): x·Wx masked to 0 + hoist (0 there) = 0 — the conv below sees the reference's zero padding
+    if (b->valid_len) { g.rows_per_batch = N; g.num_batches = BU; g.row_len = b->valid_len; }
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
   {
@@ -131,6 +166,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
     g.bias = w->conv_b[0]; g.act = F5_ACT_MISH;
     g.rows_per_batch = N; g.num_batches = BU; g.batched_tiles = 1;
     g.conv_taps = 31; g.conv_pad = 15; g.conv_grouped = 1;
+    g.row_len = b->valid_len;      // NULL, or: the second conv's input is zero on bucket rows too
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
   {
@@ -139,6 +175,10 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
     g.rows_per_batch = N; g.num_batches = BU; g.batched_tiles = 1;
     g.conv_taps = 31; g.conv_pad = 15; g.conv_grouped = 1;
     g.resid = b->h; g.ldr = D;
+    if (fused) {   // the stream's first producer: operand + statistics for block 0's attn_norm
+      g.ln_scale = (w->depth > 0 ? mod + D : mod + (size_t)w->depth * 6 * D); g.ln_stats = b->ln_stats;
+      g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+    }
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
 
@@ -146,17 +186,20 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   for (int l = 0; l < w->depth; ++l) {
     const f5_dit_block_weights& bw = w->blocks[l];
     const float* m = mod + (size_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + D, m, 0, 1, st)) return e;
+    if (!fused)
+      if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + D, m, 0, 1, st)) return e;
     {
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.qkv_w, D, R, 3 * D, D, b->qkv_bf16, 3 * D, true);
       g.bias = bw.qkv_b;
+      if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F); g.ln_tab_ld = tab_ld; }
       g.rows_per_batch = N; g.num_batches = BU;
       g.rope = b->rope; g.rope_cols = 2 * D; g.q_scale = 0.125f; g.q_cols = D;
       // weight prefetch chain (L2): while QKV runs, pull in out_w and ff1_w (contiguous in the pack)
       if (prefetch) { g.prefetch = bw.out_w; g.prefetch_bytes = (int64_t)2 * D * D; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
-    if (int e = f5_attention_fwd(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64, b->seq_len, st))
+    if (int e = f5_attention_fwd(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64,
+                                 b->seq_len ? b->seq_len : b->valid_len, st))
       return e;
     {
       f5_gemm_args g = gemm_base(b->c_bf16, D, bw.out_w, D, R, D, D, b->x, D, false);
@@ -165,12 +208,15 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.gate = m + 2 * D; g.gate_ld = 0;
       g.resid = b->x; g.ldr = D;
       if (prefetch) { g.prefetch = bw.ff1_w; g.prefetch_bytes = (int64_t)2 * F * D; }
+      if (fused) { g.ln_scale = m + 4 * D; g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D; }   // ff_norm
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
-    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + 4 * D, m + 3 * D, 0, 1, st)) return e;
+    if (!fused)
+      if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, m + 4 * D, m + 3 * D, 0, 1, st)) return e;
     {
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.ff1_w, D, R, F, D, b->ff_bf16, F, true);
       g.bias = bw.ff1_b; g.act = F5_ACT_GELU_TANH;
+      if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F) + 3 * D; g.ln_tab_ld = tab_ld; }
       if (prefetch) { g.prefetch = bw.ff2_w; g.prefetch_bytes = (int64_t)2 * D * F; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
@@ -183,6 +229,10 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       if (prefetch && l + 1 < w->depth) {
         g.prefetch = w->blocks[l + 1].qkv_w; g.prefetch_bytes = (int64_t)2 * 3 * D * D;
       }
+      if (fused) {   // next block's attn_norm scale, or norm_out's (scale first, dit.py:287)
+        g.ln_scale = (l + 1 < w->depth) ? mod + (size_t)(l + 1) * 6 * D + D : mod + (size_t)w->depth * 6 * D;
+        g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+      }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
   }
@@ -190,9 +240,11 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   // ---- AdaLayerNormZero_Final (scale first, dit.py:287) + proj_out (dit.py:398-399) ----
   {
     const float* mf = mod + (size_t)w->depth * 6 * D;
-    if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, mf, mf + D, 0, 1, st)) return e;
+    if (!fused)
+      if (int e = launch_ln_modulate(b->x, b->a_bf16, R, D, 0, mf, mf + D, 0, 1, st)) return e;
     f5_gemm_args g = gemm_base(b->a_bf16, D, w->proj_w, D, R, w->mel_dim, D, b->v, w->mel_dim, false);
     g.bias = w->proj_b;
+    if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)w->depth * (3 * D + F); g.ln_tab_ld = tab_ld; }
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
   return 0;

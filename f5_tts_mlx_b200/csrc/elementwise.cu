@@ -41,6 +41,15 @@ int launch_ln_f32(const float* x, float* y, int rows, int dim, const float* w, c
   return launch_ln_any<true>(x, y, rows, dim, 0, w, b, 0, 0, st);
 }
 
+int launch_ln_tab_prep(const float* mod, void* prep_bf16, int T, int L, int D, int NM, cudaStream_t st) {
+  ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
+  F5_REQUIRE(mod && prep_bf16 && T > 0 && L > 0, "ln_tab_prep: bad arguments");
+  F5_CHECK_CUDA(launch_kernel(ln_tab_prep_kernel, dim3(T, 2 * L + 1), dim3(256), 0, st, mod,
+                              reinterpret_cast<__nv_bfloat16*>(prep_bf16), T, L, D, NM));
+  F5_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_dwconv7_ln(const float* x, void* y, int B, int N, int C, const float* wt,
                       const float* wb, const float* ln_w, const float* ln_b, cudaStream_t st) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);

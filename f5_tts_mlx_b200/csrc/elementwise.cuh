@@ -72,6 +72,38 @@ ln_mod_kernel(const float* __restrict__ x, void* __restrict__ y, int rows,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Operand rows of the fused-AdaLN table GEMMs (f5_dit_precompute): for LN site s (2l: attn_norm of block l, 2l+1:
+// its ff_norm, 2L: norm_out) and evaluation time t, the four bf16 rows hi(1+scale), lo(1+scale), hi(shift),
+// lo(shift) with hi = bf16(v), lo = bf16(v - hi) — the GEMM against the consuming Linear's weight then yields
+// c1 = (1+scale) W^T and c2 = shift W^T to ~16 bits from bf16 tensor-core operands.
+// mod: fp32 [T, NM] (per block: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp; then norm_out's
+// scale, shift — dit.py:268,287); prep: bf16 [2L+1][4T][D].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_tab_prep_kernel(const float* __restrict__ mod, __nv_bfloat16* __restrict__ prep, int T, int L, int D, int NM) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int site = blockIdx.y, t = blockIdx.x;
+  long long off_scale, off_shift;
+  if (site < 2 * L) {
+    const long long base = (long long)(site >> 1) * 6 * D + ((site & 1) ? 3 * D : 0);
+    off_shift = base; off_scale = base + D;
+  } else {
+    off_scale = (long long)L * 6 * D; off_shift = off_scale + D;
+  }
+  const float* m = mod + (size_t)t * NM;
+  __nv_bfloat16* o = prep + ((size_t)site * 4 * T + 4 * t) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float a = 1.f + m[off_scale + c], b = m[off_shift + c];
+    const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
+    o[c] = ah;
+    o[D + c] = __float2bfloat16(a - __bfloat162float(ah));
+    o[2 * D + c] = bh;
+    o[3 * D + c] = __float2bfloat16(b - __bfloat162float(bh));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Depthwise Conv1d(k=7, pad 3, groups=C, +bias) over frames, then affine LayerNorm(eps 1e-6):
 // the first half of ConvNeXtV2Block (convnext_v2.py:35-38,48-49) and of a Vocos ConvNeXt block.
 // x: fp32 [B, N, C] channels-last; wt: fp32 [7, C] (tap-major); y: bf16 [B*N, C].

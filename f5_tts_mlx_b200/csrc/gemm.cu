@@ -19,7 +19,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, p));
+  GemmParams q = p;
+  q.prof = ps.slot;
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, q));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -45,24 +47,20 @@ static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         int n_tiles, int total_tiles, cudaStream_t stream) {
-  using S = Gemm2Smem<BN, kStages>;
+  using S = Gemm2Smem<BN, kStages, Gemm2Lno<BN, OUT_BF16>::value>;
   auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
   static SmemAttrOnce once;
   F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
-  static int num_pairs = 0;
-  if (num_pairs == 0) {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    num_pairs = sms / 2;
-  }
+  const int num_pairs = sm_count() / 2;
   const int clusters = total_tiles < num_pairs ? total_tiles : num_pairs;
   const double taps = p.conv_taps;
   ProfScope ps(PROF_GEMM, 2.0 * p.M * (double)p.N * (double)p.k_per_tap * taps,
                2.0 * ((double)p.M * p.k_per_tap + (double)p.N * p.k_per_tap * taps) +
                    (double)p.M * p.N * (OUT_BF16 ? 2.0 : 4.0),
                stream);
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), S::kTotal, stream, ta, tb, p, n_tiles, total_tiles));
+  GemmParams q = p;
+  q.prof = ps.slot;
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), S::kTotal, stream, ta, tb, q, n_tiles, total_tiles));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -127,6 +125,14 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     F5_REQUIRE(a->rope_cols % 64 == 0 && a->q_cols % 32 == 0, "f5_gemm_bf16: rope_cols/q_cols");
     F5_REQUIRE(a->act == F5_ACT_NONE && a->out_bf16, "f5_gemm_bf16: rope epilogue is bf16/no-act");
   }
+  if (a->ln_scale) {   // fused-LN producer mode
+    F5_REQUIRE(!a->out_bf16 && a->out2_bf16 && a->ln_stats, "f5_gemm_bf16: ln_scale needs an fp32 out, out2_bf16 and ln_stats");
+    F5_REQUIRE(a->n % 32 == 0 && !a->rope, "f5_gemm_bf16: ln_scale needs n %% 32 == 0");
+  }
+  if (a->ln_in_stats) {   // fused-LN consumer mode
+    F5_REQUIRE(a->ln_tab && a->ln_tab_ld >= a->n && !a->gate && taps == 1 && a->k % 64 == 0,
+               "f5_gemm_bf16: ln_in_stats needs ln_tab (ld >= n), no gate, a plain GEMM with k %% 64 == 0");
+  }
   if (a->resid) F5_REQUIRE(a->ldr % 4 == 0, "f5_gemm_bf16: ldr not multiple of 4");
   if (a->gate) F5_REQUIRE(a->gate_ld % 4 == 0, "f5_gemm_bf16: gate_ld not multiple of 4");
 
@@ -146,16 +152,19 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     // PFLOP/s vs 0.85-1.0), and for wide outputs (N >= 3072) even at M ~ 2k; the single-CTA kernel
     // with 128x128 tiles spreads small problems over more SMs.
     const long long pair_tiles = (long long)cdiv(a->m, 256) * cdiv(a->n, 256);
-    variant = (a->n >= 128 && (pair_tiles >= 148 || (pair_tiles >= 74 && a->n >= 3072))) ? 2 : 1;
+    const int sms = sm_count();
+    variant = (a->n >= 128 && (pair_tiles >= sms || (pair_tiles >= sms / 2 && a->n >= 3072))) ? 2 : 1;
   }
+  if (variant == 2 && a->ln_scale && a->tile_n != 0 && a->tile_n != 256) variant = 1;   // pair kernel: LN producer mode with 256-wide tiles only
+  if (variant == 2 && a->ln_scale && !(a->n % 256 == 0 || a->n >= 1024)) variant = 1;
   if (variant == 2) {
     int bn2 = a->tile_n;
     if (bn2 == 0) bn2 = (a->n % 256 == 0 || a->n >= 1024) ? 256 : 128;
     // wide outputs on few row tiles (QKV at batch 1: 8 x 12 tiles of 256 columns on 74 SM pairs = two
     // rounds, the second 30 % full): 192-column tiles give 8 x 16 smaller tiles
-    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0) {
+    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0 && !a->ln_scale) {
       const int t256 = cdiv(a->m, 256) * cdiv(a->n, 256), t192 = cdiv(a->m, 256) * cdiv(a->n, 192);
-      const int pairs = 74;
+      const int pairs = sm_count() / 2;
       const double c256 = (double)cdiv(t256, pairs) * 256, c192 = (double)cdiv(t192, pairs) * 192;
       if (c192 < 0.85 * c256) bn2 = 192;   // only when it removes a mostly-empty round
     }
@@ -176,6 +185,9 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     p2.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
     p2.w_static = a->w_static;
     p2.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p2.pf_bytes = a->prefetch_bytes;
+    p2.ln_scale = a->ln_scale; p2.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
+    p2.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p2.ln_in_units = a->k / 32;
+    p2.ln_tab = a->ln_tab; p2.ln_tab_ld = a->ln_tab_ld;
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
     {
@@ -207,7 +219,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   if (bn == 0) {
     // fill the 148 SMs: prefer 128-wide tiles unless that leaves most SMs idle
     const int mt = batched ? nb * cdiv(rpb, 128) : cdiv(a->m, 128);
-    bn = (mt * cdiv(a->n, 128) >= 120 || a->n <= 64) ? 128 : 64;
+    bn = (mt * cdiv(a->n, 128) >= (sm_count() * 13) / 16 || a->n <= 64) ? 128 : 64;
     if (a->n <= 64) bn = 64;
   }
   F5_REQUIRE(bn == 64 || bn == 128, "f5_gemm_bf16: tile_n must be 64 or 128");
@@ -235,6 +247,9 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   p.ts = reinterpret_cast<unsigned long long*>(a->debug_ts);
   p.w_static = a->w_static;
   p.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p.pf_bytes = a->prefetch_bytes;
+  p.ln_scale = a->ln_scale; p.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
+  p.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p.ln_in_units = a->k / 32;
+  p.ln_tab = a->ln_tab; p.ln_tab_ld = a->ln_tab_ld;
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows
@@ -259,7 +274,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   const bool rope = a->rope != nullptr;
   // grids that fit in one wave leave one CTA per SM anyway: spend the whole smem on a 6-stage ring
   // (192 KB in flight per SM instead of 96 KB) to cover the L2/HBM latency of the operand stream
-  if (bn == 128 && (long long)grid.x * grid.y <= 148)
+  if (bn == 128 && (long long)grid.x * grid.y <= sm_count())
     return dispatch_epi<128, 6>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
   if (bn == 128) return dispatch_epi<128, 3>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
   return dispatch_epi<64, 4>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);

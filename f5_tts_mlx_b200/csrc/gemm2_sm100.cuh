@@ -88,16 +88,26 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
                : "memory");
 }
 
-template <int BN, int kStages>
+// LNO: the instantiation supports the fused-LN producer mode (fp32 output, 256-wide tiles): a third column vector
+// (1 + scale) per accumulator stage and one 8 KB bf16 staging buffer per epilogue group
+template <int BN, int kStages, bool LNO = false>
 struct Gemm2Smem {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = (BN / 2) * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
-  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN])
-  static constexpr int kStageOutOffset = (kColsOffset + 4 * BN * 4 + 127) & ~127;   // 2 x 16 KB store staging
-  static constexpr int kTotal = kStageOutOffset + 2 * 32768 + 1024;  // 2 epilogue groups x (2 x 16 KB) + align slack
+  static constexpr int kColVecs = LNO ? 3 : 2;
+  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN][, scale_s[BN]])
+  static constexpr int kStageOutOffset = (kColsOffset + 2 * kColVecs * BN * 4 + 1023) & ~1023;   // 2 x 16 KB store staging per group
+  static constexpr int kStage2Offset = kStageOutOffset + 2 * 32768;                  // 8 KB per group (LNO)
+  static constexpr int kTotal = kStage2Offset + (LNO ? 2 * 8192 : 0) + 1024;  // + align slack
+  static_assert(kTotal <= 232448, "CTA-pair GEMM: shared memory over the 227 KB limit");
+};
+
+template <int BN, bool OUT_BF16>
+struct Gemm2Lno {
+  static constexpr bool value = !OUT_BF16 && BN == 256;
 };
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
@@ -105,7 +115,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
                      const int n_tiles, const int total_tiles) {
-  using S = Gemm2Smem<BN, kStages>;
+  constexpr bool LNO = Gemm2Lno<BN, OUT_BF16>::value;
+  using S = Gemm2Smem<BN, kStages, LNO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -159,7 +170,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   }
   pdl_wait();
-  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 2);
+  if (threadIdx.x == 0) { ts_mark(p, blockIdx.x, 2); prof_stamp_begin(p.prof); }
 
   // register hand-over (384 threads cap every thread at 168): warps 0-3 need few, the epilogue warps hold a
   // row's RoPE table, residual and accumulator chunk.  128 x 40 + 256 x 232 <= 64 K registers.
@@ -268,9 +279,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
 
       // operand staging for this tile (overlaps the MMAs still filling the accumulator)
-      float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * 2 * BN;
+      float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * S::kColVecs * BN;
       float* gate_s = bias_s + BN;
-      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s);   // both groups write the same values
+      float* scale_s = LNO ? gate_s + BN : nullptr;
+      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, scale_s);   // both groups write the same values
+      float ln_mu_r, ln_rstd;
+      epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
       float2 cs[ROPE ? 32 : 1];
       epi_load_rope<ROPE>(p, pos, cs);
       float4 res0[8];
@@ -287,6 +301,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.bar_id = 1 + grp;
       stg.probe_cta = blockIdx.x;
       stg.r = lg * 32 + lane;
+      stg.buf2 = LNO ? smem + S::kStage2Offset + grp * 8192 : nullptr;
+      stg.buf2_par = 0;
+      stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
       if (pair_tiles_per_batch > 0) {
         const int m0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
         stg.row0 = (long long)b_idx_tile * p.rows_per_batch + m0;
@@ -296,7 +313,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         stg.rows_valid = min(128, p.M - (int)stg.row0);
       }
       epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
-                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg, grp, 2);
+                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg, grp, 2,
+                                              scale_s);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
@@ -310,7 +328,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, BN > 128 ? 512 : 256);
   }
-  if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 9);
+  if (threadIdx.x == 0) { ts_mark(p, blockIdx.x, 9); prof_stamp_end(p.prof); }
 }
 
 }  // namespace f5

@@ -34,9 +34,21 @@ struct GemmParams {
   __nv_bfloat16* out2;     // optional bf16 copy of the result
   int ldo2;
   unsigned long long* ts;  // debug: per-CTA phase timestamps (globaltimer ns), 10 slots per CTA, or null
+  unsigned long long* prof;  // in-graph timing slot (ptx.cuh prof_stamp_*), or null
   int w_static;            // B operand may be fetched before the PDL wait (weights)
   const char* pf_ptr;      // weights of a LATER GEMM to pull into L2 while this one runs, or null
   long long pf_bytes;
+  // ---- fused AdaLayerNormZero (dit.py:270,289,321), by linearity of the consuming Linear ----
+  //   Linear(LN(x) (1+s) + b) = rstd * ( (x (1+s)) W^T - mean * c1 ) + c2,  c1 = (1+s) W^T,  c2 = b W^T + bias
+  // producer side (this GEMM writes the fp32 residual stream x): out2 <- bf16(x * (1 + ln_scale[col])) through the
+  // staged store path, ln_stats[row][col/32] <- (mean, M2) of each 32-column chunk of the row
+  const float* ln_scale;   // [N] scale vector of the NEXT AdaLN, or null
+  float2* ln_stats;        // [rows][N/32]
+  // consumer side (A is such an out2 matrix): the epilogue finishes the LayerNorm
+  const float2* ln_in_stats;  // [rows][K/32] or null
+  int ln_in_units;            // K/32
+  const float* ln_tab;        // 4 rows of ln_tab_ld floats: c1_hi, c1_lo, c2_hi, c2_lo (bf16-split operand rows of
+  long long ln_tab_ld;        //   the table GEMM), already offset to this GEMM's column 0
 };
 
 // Each CTA touches its 1/num_ctas slice of [pf_ptr, pf_ptr + pf_bytes) with L2 prefetches (one warp,
@@ -89,15 +101,47 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 // stage bias[n0..n0+BN) and gate[n0..n0+BN) (gate only when it is shared by all utterances,
 // gate_ld == 0) into shared memory; called by the 128 epilogue threads, `et` = 0..127
+// With the fused-LN consumer mode gate_s holds c1 and bias_s holds c2 + bias (such GEMMs have no gate); with the
+// producer mode scale_s (may be null when the instantiation has no fp32 output) holds 1 + ln_scale.
 template <int BN>
 __device__ __forceinline__ void epi_stage_cols(const GemmParams& p, int n0, int et, float* bias_s,
-                                               float* gate_s) {
+                                               float* gate_s, float* scale_s = nullptr) {
 #pragma unroll
   for (int i = et; i < BN; i += 128) {
     const int col = n0 + i;
-    bias_s[i] = (p.bias != nullptr && col < p.N) ? p.bias[col] : 0.f;
-    gate_s[i] = (p.gate != nullptr && p.gate_ld == 0 && col < p.N) ? p.gate[col] : 1.f;
+    const bool ok = col < p.N;
+    float b = (p.bias != nullptr && ok) ? p.bias[col] : 0.f;
+    float g = (p.gate != nullptr && p.gate_ld == 0 && ok) ? p.gate[col] : 1.f;
+    if (p.ln_in_stats != nullptr && ok) {
+      const float* t = p.ln_tab + col;
+      g = t[0] + t[p.ln_tab_ld];
+      b += t[2 * p.ln_tab_ld] + t[3 * p.ln_tab_ld];
+    }
+    bias_s[i] = b;
+    gate_s[i] = g;
+    if (scale_s != nullptr) scale_s[i] = (p.ln_scale != nullptr && ok) ? 1.f + p.ln_scale[col] : 1.f;
   }
+}
+
+// consumer side of the fused LN: combine the row's per-chunk (mean, M2) pairs (equal counts of 32, fixed order =>
+// deterministic) into (mean * rstd, rstd); eps as nn.LayerNorm(eps=1e-6) (dit.py:262,281)
+__device__ __forceinline__ void epi_load_ln_row(const GemmParams& p, int row, bool row_ok, float& mu_r, float& rstd) {
+  mu_r = 0.f; rstd = 1.f;
+  if (p.ln_in_stats == nullptr || !row_ok) return;
+  const float4* st = reinterpret_cast<const float4*>(p.ln_in_stats + (size_t)row * p.ln_in_units);
+  float mean = 0.f, m2 = 0.f;
+  for (int u = 0; u < p.ln_in_units; u += 2) {
+    const float4 v = st[u >> 1];                       // (mean, M2) of chunks u and u + 1
+    const float inv0 = __fdividef(1.f, (float)(u + 1)), inv1 = __fdividef(1.f, (float)(u + 2));
+    float d = v.x - mean;
+    mean = fmaf(d, inv0, mean);
+    m2 += v.y + d * d * (32.f * u) * inv0;
+    d = v.z - mean;
+    mean = fmaf(d, inv1, mean);
+    m2 += v.w + d * d * (32.f * (u + 1)) * inv1;
+  }
+  rstd = rsqrtf(m2 / (32.f * p.ln_in_units) + 1e-6f);
+  mu_r = mean * rstd;
 }
 
 template <bool ROPE>
@@ -138,11 +182,17 @@ struct EpiStage {
   int rows_valid;          // rows of the tile that exist
   int bar_id;              // named barrier of this group of 4 epilogue warps (1 + group)
   int probe_cta;           // debug (F5_EPI_PROBE builds): linear CTA id for sub-step stamps
+  // fused-LN producer mode: staging of the bf16 copy (8 KB per chunk); buf2_par = 8192 when two buffers alternate,
+  // 0 when there is room for one only (then a second barrier per chunk guards its reuse)
+  uint8_t* buf2;
+  int buf2_par;
+  float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics
 };
 
+// `w2` (fused-LN producer mode, fp32 output only): the chunk's bf16 copy, 4 x uint4 per row, stored to p.out2
 template <bool OUT_BF16>
 __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const EpiStage& st, int par,
-                                                 const GemmParams& p, int col0) {
+                                                 const GemmParams& p, int col0, const uint4* w2 = nullptr) {
   uint8_t* buf = st.buf + par * 16384;
   if (OUT_BF16) {
     uint8_t* mine = buf + st.r * 64;
@@ -166,6 +216,14 @@ __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const Epi
   } else {
     uint8_t* mine = buf + st.r * 128;
     const int sw = st.r & 7;
+    uint8_t* buf2 = st.buf2 + par * st.buf2_par;
+    if (w2 != nullptr) {
+      if (st.buf2_par == 0) asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");   // previous chunk's readers done
+      uint8_t* mine2 = buf2 + st.r * 64;
+      const int sw2 = (st.r >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(mine + ((j ^ sw) * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -180,6 +238,17 @@ __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const Epi
         *reinterpret_cast<float4*>(out + (size_t)(st.row0 + row) * p.ldo + col0 + q * 4) = w;
       }
     }
+    if (w2 != nullptr) {
+      const int q2 = st.et & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 32 + (st.et >> 2);
+        if (row < st.rows_valid && col0 + q2 * 8 < p.N) {
+          const uint4 w = *reinterpret_cast<const uint4*>(buf2 + row * 64 + ((q2 ^ ((row >> 1) & 3)) * 16));
+          *reinterpret_cast<uint4*>(p.out2 + (size_t)(st.row0 + row) * p.ldo2 + col0 + q2 * 8) = w;
+        }
+      }
+    }
   }
 }
 
@@ -189,15 +258,28 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
                                           const float* bias_s, const float* gate_s,
                                           const float2 (&cs)[ROPE ? 32 : 1], const GemmParams& p,
                                           int col0, int row, int b_idx, bool row_ok, bool row_valid,
-                                          const EpiStage& st) {
+                                          const EpiStage& st, const float* scale_s = nullptr) {
   float v[32];
+  if (p.ln_in_stats != nullptr) {
+    // fused-LN consumer: rstd * acc - (mean * rstd) * c1 + (c2 + bias)   (gate_s = c1, bias_s = c2 + bias)
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
-    v[j] = __uint_as_float(acc[j]) + bb.x;
-    v[j + 1] = __uint_as_float(acc[j + 1]) + bb.y;
-    v[j + 2] = __uint_as_float(acc[j + 2]) + bb.z;
-    v[j + 3] = __uint_as_float(acc[j + 3]) + bb.w;
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+      const float4 cc = *reinterpret_cast<const float4*>(gate_s + j);
+      v[j] = fmaf(__uint_as_float(acc[j]), st.rstd, fmaf(-st.mu_r, cc.x, bb.x));
+      v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), st.rstd, fmaf(-st.mu_r, cc.y, bb.y));
+      v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), st.rstd, fmaf(-st.mu_r, cc.z, bb.z));
+      v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), st.rstd, fmaf(-st.mu_r, cc.w, bb.w));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+      v[j] = __uint_as_float(acc[j]) + bb.x;
+      v[j + 1] = __uint_as_float(acc[j + 1]) + bb.y;
+      v[j + 2] = __uint_as_float(acc[j + 2]) + bb.z;
+      v[j + 3] = __uint_as_float(acc[j + 3]) + bb.w;
+    }
   }
   if (ACT == ACT_GELU_TANH) {
 #pragma unroll
@@ -228,7 +310,7 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
-  if (p.gate != nullptr) {
+  if (p.gate != nullptr && p.ln_in_stats == nullptr) {
     if (p.gate_ld == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -245,6 +327,30 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+  }
+  if constexpr (!OUT_BF16) {
+    if (p.ln_scale != nullptr && st.buf != nullptr) {
+      // fused-LN producer: statistics of this 32-column chunk of the finished residual-stream row, and the bf16
+      // operand x * (1 + scale) of the GEMM that consumes LN(x)
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+      const float mean = sum * (1.f / 32.f);
+      float m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
+      if (row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 5) + (col0 >> 5)] = make_float2(mean, m2);
+      uint4 w2[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 s0 = *reinterpret_cast<const float4*>(scale_s + 8 * j);
+        const float4 s1 = *reinterpret_cast<const float4*>(scale_s + 8 * j + 4);
+        w2[j] = make_uint4(pack_bf16x2(v[8 * j] * s0.x, v[8 * j + 1] * s0.y), pack_bf16x2(v[8 * j + 2] * s0.z, v[8 * j + 3] * s0.w),
+                           pack_bf16x2(v[8 * j + 4] * s1.x, v[8 * j + 5] * s1.y), pack_bf16x2(v[8 * j + 6] * s1.z, v[8 * j + 7] * s1.w));
+      }
+      epi_store_staged<OUT_BF16>(v, st, HALF, p, col0, w2);
+      return;
+    }
   }
   if (st.buf != nullptr) {
     if (p.out2 != nullptr && row_ok) {
@@ -297,7 +403,8 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
                                                const float* gate_s, const float2 (&cs)[ROPE ? 32 : 1],
                                                float4 (&res0)[8], const GemmParams& p, int n0, int row,
                                                int b_idx, bool row_ok, bool row_valid,
-                                               const EpiStage& st, int cc0 = 0, int cc_step = 1) {
+                                               const EpiStage& st, int cc0 = 0, int cc_step = 1,
+                                               const float* scale_s = nullptr) {
   float4 res1[8];
 #pragma unroll 1
   for (int cc = cc0; cc < BN / 64; cc += cc_step) {
@@ -309,14 +416,14 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
     tmem_wait_ld();
     if (colA < p.N)   // uniform per CTA
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
-                                        b_idx, row_ok, row_valid, st);
+                                        b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 : nullptr);
     // chunk B: request the next unit's first residual, then drain B
     if (cc + cc_step < BN / 64) epi_load_resid(p, row, colA + 64 * cc_step, row_ok, res0);
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res1, bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs, p,
-                                        colB, row, b_idx, row_ok, row_valid, st);
+                                        colB, row, b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 + 32 : nullptr);
   }
 }
 
@@ -330,7 +437,8 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
                                                          const float2 (&cs)[ROPE ? 32 : 1],
                                                          float4 (&res)[BN / 32][8], const GemmParams& p,
                                                          int n0, int row, int b_idx, bool row_ok,
-                                                         bool row_valid, const EpiStage& st) {
+                                                         bool row_valid, const EpiStage& st,
+                                                         const float* scale_s = nullptr) {
 #pragma unroll
   for (int cc = 0; cc < BN / 64; ++cc) {
     const int colA = n0 + cc * 64, colB = colA + 32;
@@ -342,7 +450,7 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
 #endif
     if (colA < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
-                                        b_idx, row_ok, row_valid, st);
+                                        b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 : nullptr);
 #ifdef F5_EPI_PROBE
     if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 4);
 #endif
@@ -350,7 +458,7 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
     tmem_wait_ld();
     if (colB < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res[2 * cc + 1], bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs,
-                                        p, colB, row, b_idx, row_ok, row_valid, st);
+                                        p, colB, row, b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 + 32 : nullptr);
   }
 }
 

@@ -36,8 +36,11 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kColsOffset = (kBarOffset + (2 * kStages + 1) * 8 + 16 + 15) & ~15;   // bias_s[BN], gate_s[BN] (float4 reads)
-  static constexpr int kTotal = kColsOffset + 2 * BN * 4 + 1024;  // + align slack
+  static constexpr int kColsOffset = (kBarOffset + (2 * kStages + 1) * 8 + 16 + 15) & ~15;   // bias_s[BN], gate_s[BN], scale_s[BN] (float4 reads)
+  static constexpr int kTotal = kColsOffset + 3 * BN * 4 + 1024;  // + align slack
+  // epilogue store staging reuses the (idle) operand ring: fp32/bf16 chunks at [0, 64 KB) (32 KB per group), the
+  // bf16 copy of the fused-LN producer mode at [64 KB, 96 KB) (16 KB per group, two alternating 8 KB buffers)
+  static_assert(kStages * kStageBytes >= 98304, "operand ring too small for the epilogue staging");
 };
 
 // Epilogue groups: 4 warps cover the 128 accumulator rows (TMEM lane quarter = warp % 4).  With 128-column
@@ -116,7 +119,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   }
   pdl_wait();   // predecessor's outputs (our A operand / residual) are complete and visible
-  if (threadIdx.x == 0) ts_mark(p, cta_lin, 2);
+  if (threadIdx.x == 0) { ts_mark(p, cta_lin, 2); prof_stamp_begin(p.prof); }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -198,7 +201,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     // operand staging, overlapped with the main loop
     float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + grp * BNG;
     float* gate_s = reinterpret_cast<float*>(smem + S::kColsOffset) + BN + grp * BNG;
-    epi_stage_cols<BNG>(p, n0g, et, bias_s, gate_s);
+    float* scale_s = OUT_BF16 ? nullptr : reinterpret_cast<float*>(smem + S::kColsOffset) + 2 * BN + grp * BNG;
+    epi_stage_cols<BNG>(p, n0g, et, bias_s, gate_s, scale_s);
+    float ln_mu_r, ln_rstd;
+    epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
     float2 cs[ROPE ? 32 : 1];
     epi_load_rope<ROPE>(p, pos, cs);
     constexpr bool kPreloadAll = (kStages > 4);   // single-wave variant: one CTA per SM
@@ -228,13 +234,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.rows_valid = p.tiles_per_batch > 0 ? min(128, p.rows_per_batch - m_in_batch0) : min(128, p.M - row0);
       stg.bar_id = 1 + grp;
       stg.probe_cta = cta_lin;
+      stg.buf2 = smem + 65536 + grp * 16384;
+      stg.buf2_par = 8192;
+      stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
       const uint32_t tacc = tmem_base + grp * BNG + ((uint32_t)(lg * 32) << 16);
       if constexpr (kPreloadAll) {
         epi_drain_tile_preloaded<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all, p, n0g, row, b_idx,
-                                                           row_ok, row_valid, stg);
+                                                           row_ok, row_valid, stg, scale_s);
       } else {
         epi_drain_tile<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all[0], p, n0g, row, b_idx, row_ok,
-                                                 row_valid, stg);
+                                                 row_valid, stg, 0, 1, scale_s);
       }
     }
     tc_fence_before();
@@ -246,7 +255,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
-  if (threadIdx.x == 0) ts_mark(p, cta_lin, 9);
+  if (threadIdx.x == 0) { ts_mark(p, cta_lin, 9); prof_stamp_end(p.prof); }
 }
 
 }  // namespace f5

@@ -30,6 +30,17 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+int sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = sms;
+  return sms;
+}
+
 int device_check() {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
@@ -104,9 +115,20 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::atomic<long long> g_launches{0};
+struct GraphSlotMeta { int kind; double flops, bytes; };
+static unsigned long long* g_gslots = nullptr;
+static int g_gslots_cap = 0;
+static std::vector<GraphSlotMeta> g_gmeta;
 
-ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st) : idx_(-1), st_(st) {
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st) : idx_(-1), st_(st), slot(nullptr) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_gslots != nullptr) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if ((int)g_gmeta.size() < g_gslots_cap) {
+      slot = g_gslots + 2 * g_gmeta.size();
+      g_gmeta.push_back({kind, flops, bytes});
+    }
+  }
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
@@ -132,6 +154,27 @@ int f5_prof_enable(int on) {
   f5::g_prof.clear();
   f5::g_prof_on = on != 0;
   return 0;
+}
+// In-graph timing: install a device buffer of `max_slots` x 2 uint64 (the caller fills [*,0] with UINT64_MAX and
+// [*,1] with 0 before each run); slot i belongs to the i-th ProfScope opened from now on.  NULL uninstalls.
+int f5_prof_graph_begin(void* slots, int32_t max_slots) {
+  std::lock_guard<std::mutex> lk(f5::g_prof_mu);
+  f5::g_gslots = reinterpret_cast<unsigned long long*>(slots);
+  f5::g_gslots_cap = slots ? max_slots : 0;
+  if (slots) f5::g_gmeta.clear();
+  return 0;
+}
+// kind (PROF_* : 0 gemm, 1 attention, 2 ln_modulate, 3 other) and algorithmic flops / bytes of every slot handed out
+// since the last f5_prof_graph_begin; returns the slot count
+int f5_prof_graph_meta(int32_t* kinds, double* flops, double* bytes, int32_t cap) {
+  std::lock_guard<std::mutex> lk(f5::g_prof_mu);
+  const int n = (int)f5::g_gmeta.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (kinds) kinds[i] = f5::g_gmeta[i].kind;
+    if (flops) flops[i] = f5::g_gmeta[i].flops;
+    if (bytes) bytes[i] = f5::g_gmeta[i].bytes;
+  }
+  return n;
 }
 // out: [kinds][4] = {milliseconds, flops, bytes, launches}
 int f5_prof_summary(double* out, int kinds) {
@@ -160,6 +203,6 @@ int f5_struct_sizes(int32_t* out, int32_t n) {
   return 10;
 }
 const char* f5_last_error(void) { return f5::g_err; }
-int f5_abi_version(void) { return 1000; }
+int f5_abi_version(void) { return 1100; }
 int f5_device_check(void) { return f5::device_check(); }
 }

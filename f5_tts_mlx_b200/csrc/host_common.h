@@ -36,6 +36,9 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs)
+int sm_count();
+
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh); F5_PDL=0 disables it.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
@@ -75,11 +78,15 @@ inline cudaError_t ensure_dyn_smem(SmemAttrOnce& once, K kern, int bytes) {
 // when profiling is enabled (f5_prof_enable) a CUDA event pair brackets the launch on its stream
 // and f5_prof_summary returns the summed device time / algorithmic FLOPs / bytes per family.
 enum ProfKind { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NKINDS = 4 };
+// In-graph timing (f5_prof_graph_begin): while a slot buffer is installed every ProfScope also hands its kernel one
+// slot of two uint64 — [0] atomicMin(globaltimer) when a CTA has passed its dependency wait, [1] atomicMax at CTA
+// exit — whose address is baked into a captured CUDA graph, so one replay yields every kernel's in-situ duration.
 struct ProfScope {
   ProfScope(int kind, double flops, double bytes, cudaStream_t st);
   ~ProfScope();
   int idx_;
   cudaStream_t st_;
+  unsigned long long* slot;   // device pointer or nullptr
 };
 
 }  // namespace f5

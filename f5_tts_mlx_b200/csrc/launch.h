@@ -37,6 +37,7 @@ int launch_cast_pad_bf16(const float* src, int d, void* dst, int ld, int rows,
 int launch_concat_cond_text(const float* cond, int dc, int Bc, int N, const float* text, int dt,
                             void* dst, int ld, int rows, int drop_from_row, cudaStream_t st,
                             const int* cond_len = nullptr);
+int launch_ln_tab_prep(const float* mod, void* prep_bf16, int T, int L, int D, int NM, cudaStream_t st);
 int launch_duration_head(const float* x, int B, int N, int D, const int* len, const float* norm_w,
                          const float* pred_w, float* out, cudaStream_t st);
 }  // namespace f5

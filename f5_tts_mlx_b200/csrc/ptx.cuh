@@ -43,6 +43,23 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 
+// in-graph kernel timing (host_common.h, ProfScope::slot): [0] <- min over CTAs of the time a CTA proceeds past its
+// dependency wait, [1] <- max over CTAs of the exit time (fire-and-forget reductions, one thread per CTA)
+__device__ __forceinline__ void prof_stamp_begin(unsigned long long* slot) {
+  if (slot != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(slot, t);
+  }
+}
+__device__ __forceinline__ void prof_stamp_end(unsigned long long* slot) {
+  if (slot != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(slot + 1, t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

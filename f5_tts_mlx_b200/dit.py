@@ -26,6 +26,8 @@ class DitBuffersC(C.Structure):
         ("grn_nx", C.c_void_p), ("ct_bf16", C.c_void_p), ("silu_t", C.c_void_p),
         ("y_bf16", C.c_void_p), ("x", C.c_void_p), ("h", C.c_void_p), ("a_bf16", C.c_void_p),
         ("c_bf16", C.c_void_p), ("qkv_bf16", C.c_void_p), ("ff_bf16", C.c_void_p), ("v", C.c_void_p),
+        ("ln_stats", C.c_void_p), ("ln_tab", C.c_void_p), ("ln_prep", C.c_void_p),
+        ("valid_len", C.c_void_p),
     ]
 
 
@@ -44,7 +46,7 @@ class DitSession:
     evaluation times, with or without the CFG batch doubling."""
 
     def __init__(self, cfg: DiTConfig, ct_ld: int, batch: int, frames: int, n_times: int, use_cfg: bool,
-                 text_cols: int, device: torch.device, masked: bool):
+                 text_cols: int, device: torch.device, masked: bool, fused_adaln: bool = True):
         self.cfg, self.batch, self.frames, self.n_times, self.use_cfg = cfg, batch, frames, n_times, use_cfg
         self.device = device
         D, F, Ct = cfg.dim, cfg.ff_inner, cfg.text_dim
@@ -56,6 +58,8 @@ class DitSession:
         self.text = z(batch, max(text_cols, 1), dt=i32)
         self.text_len = z(BU, dt=i32)
         self.seq_len = z(BU, dt=i32) if masked else None
+        self.valid_len_buf = torch.full((BU,), frames, dtype=i32, device=device)   # frame bucketing (f5_dit_buffers.valid_len)
+        self.valid_len = None
         self.cond = z(batch, frames, cfg.mel_dim)
         self.tvals = z(n_times)
         self.rope = rope_table(frames, cfg.dim_head).to(device)
@@ -77,6 +81,12 @@ class DitSession:
         self.qkv_bf16 = z(R, 3 * D, dt=bf16)
         self.ff_bf16 = z(R, F, dt=bf16)
         self.v = z(R, cfg.mel_dim)
+        # fused AdaLN (f5_gemm_args.ln_*): per-row chunk statistics, the c1/c2 operand tables of every consuming
+        # Linear for every evaluation time, and the bf16 operand rows of the table GEMMs
+        self.ln_tab_ld = cfg.depth * (3 * D + F) + 128
+        self.ln_stats = z(R, D // 32, 2) if fused_adaln else None
+        self.ln_tab = z(4 * n_times, self.ln_tab_ld) if fused_adaln else None
+        self.ln_prep = z(2 * cfg.depth + 1, 4 * n_times, D, dt=bf16) if fused_adaln else None
         c = DitBuffersC()
         c.batch, c.frames, c.cfg, c.n_times = batch, frames, int(use_cfg), n_times
         c.text_len_max, c.drop_flags = self.text.shape[1], 0
@@ -85,14 +95,23 @@ class DitSession:
             setattr(c, name, t.data_ptr() if t is not None else None)
         self.c = c
 
+    def use_bucketing(self) -> None:
+        """Bind the valid-length buffer: from now on `frames` is a bucket size and set_inputs(frames_valid=N) says
+        how many rows are real (must be called before the plan's graph is captured)."""
+        self.valid_len = self.valid_len_buf
+        self.c.valid_len = self.valid_len_buf.data_ptr()
+
     def set_inputs(self, text: torch.Tensor, cond: torch.Tensor, tvals: torch.Tensor,
-                   seq_len: Optional[torch.Tensor]) -> None:
+                   seq_len: Optional[torch.Tensor], frames_valid: Optional[int] = None) -> None:
         """text int [batch, nt] (pad -1), cond fp32 [batch, frames, mel], tvals fp32 [n_times],
-        seq_len int [batch] or None."""
+        seq_len int [batch] or None; frames_valid: real frames per utterance when `frames` is a bucket."""
         B = self.batch
         assert text.shape == self.text.shape, (text.shape, self.text.shape)
+        nv = self.frames if frames_valid is None else int(frames_valid)
+        assert 0 < nv <= self.frames and (nv == self.frames or self.valid_len is not None)
+        self.valid_len_buf.fill_(nv)
         self.text.copy_(text.to(torch.int32))
-        tl = (text != -1).sum(dim=-1).clamp(max=self.frames).to(torch.int32)
+        tl = (text != -1).sum(dim=-1).clamp(max=nv).to(torch.int32)
         self.text_len[:B].copy_(tl)
         if self.use_cfg:
             self.text_len[B:].copy_(tl)
@@ -121,11 +140,13 @@ class DiT:
 
     def __init__(self, *, dim, depth=8, heads=8, dim_head=64, dropout=0.0, ff_mult=4, mel_dim=100,
                  text_num_embeds=256, text_dim=None, text_mask_padding=True, conv_layers=0,
-                 device: str | torch.device = "cuda"):
+                 device: str | torch.device = "cuda", fused_adaln: bool = True):
         if text_dim is None:
             text_dim = mel_dim
         if dim_head != 64 or dim != heads * dim_head:
             raise ValueError("libf5b200 supports dim_head == 64 and dim == heads * 64")
+        if dim % 128 != 0 or not (256 <= dim <= 1024):
+            raise ValueError("libf5b200 supports 256 <= dim <= 1024, dim a multiple of 128 (see check_common in csrc/dit.cu)")
         if not text_mask_padding:
             raise NotImplementedError("text_mask_padding=False is not on the accelerated path")
         if dropout != 0.0:
@@ -134,9 +155,13 @@ class DiT:
                                 mel_dim=mel_dim, text_num_embeds=text_num_embeds, text_dim=text_dim,
                                 conv_layers=conv_layers, text_mask_padding=text_mask_padding)
         self.dim, self.depth = dim, depth
+        # AdaLN LayerNorm+modulate folded into the neighbouring GEMM epilogues (default); False keeps the separate
+        # f5_ln_modulate launches (the r01 path — kept for A/B measurements and as a cross-check in the tests)
+        self.fused_adaln = bool(fused_adaln)
         self.device = torch.device(device)
         self.packed: Optional[PackedDiT] = None
         self._sessions: Dict[tuple, DitSession] = {}
+        self.session_cache_size = 12
 
     # -- weights --
     def load_weights(self, weights: Weights | list) -> "DiT":
@@ -160,16 +185,23 @@ class DiT:
 
     # -- sessions --
     def session(self, batch: int, frames: int, n_times: int, use_cfg: bool, text_cols: int,
-                masked: bool) -> DitSession:
-        key = (batch, frames, n_times, use_cfg, text_cols, masked)
-        s = self._sessions.get(key)
+                masked: bool, bucketed: bool = False) -> DitSession:
+        key = (batch, frames, n_times, use_cfg, text_cols, masked, self.fused_adaln, bucketed)
+        s = self._sessions.pop(key, None)
         if s is None:
-            if len(self._sessions) >= 4:
+            while len(self._sessions) >= self.session_cache_size:
                 self._sessions.pop(next(iter(self._sessions)))
             s = DitSession(self.config, self._require_weights().ct_ld, batch, frames, n_times, use_cfg,
-                           text_cols, self.device, masked)
-            self._sessions[key] = s
+                           text_cols, self.device, masked, self.fused_adaln)
+            if bucketed:
+                s.use_bucketing()
+        self._sessions[key] = s          # LRU order: most recently used last
         return s
+
+    def release_session(self, s: DitSession) -> None:
+        for k, v in list(self._sessions.items()):
+            if v is s:
+                del self._sessions[k]
 
     def precompute(self, s: DitSession) -> None:
         lib = _lib.load()

@@ -93,14 +93,20 @@ def generate(
     output_path: Optional[str] = None,
     f5tts: Optional[F5TTS] = None,
     batch_sentences: bool = False,
+    frame_bucket: int = 128,
 ):
     """generate.py:113-244.  Extensions: `f5tts` reuses a loaded model; `batch_sentences=True` runs all
     sentences as ONE ragged `sample()` batch instead of the reference's serial loop (SURVEY §8f row 2;
     numerically it differs from the serial loop only through the reference's own padding caveat — GRN
-    statistics and the ODE on padded frames see the batch-maximum length)."""
+    statistics and the ODE on padded frames see the batch-maximum length); `frame_bucket` (default 128 frames) lets
+    the sentences of the serial loop share one set of buffers and ONE captured CUDA graph per length bucket instead of
+    re-capturing for every distinct length (0 = the exact shapes); results are unchanged (F5TTS.sample)."""
     if f5tts is None:
         f5tts = F5TTS.from_pretrained(model_name, quantization_bits=quantization_bits)
     dev = f5tts.transformer.device
+    if f5tts._vocoder is None:
+        raise ValueError("generate() needs a model with a vocoder (F5TTS(..., vocoder=Vocos(...).decode)); "
+                         "without one sample() returns mel spectrograms, not a waveform")
     if ref_audio_path is None:
         raise ValueError("ref_audio_path is required (the reference's packaged default clip is not redistributed here)")
     audio, sr = read_wav(ref_audio_path)
@@ -154,7 +160,7 @@ def generate(
         text = convert_char_to_pinyin([ref_audio_text + " " + sentence])
         wave, _ = f5tts.sample(audio_d[None], text=text, duration=frames, steps=steps, method=method, speed=speed,
                                cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, seed=seed,
-                               return_trajectory=False)
+                               return_trajectory=False, frame_bucket=frame_bucket)
         waves.append(wave[audio.shape[0]:])                                       # strip the reference (generate.py:183)
     wave = torch.cat(waves, dim=0)
     if wave.is_cuda:

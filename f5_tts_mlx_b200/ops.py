@@ -55,8 +55,13 @@ def gemm(
     tile_n: int = 0,
     variant: int = 0,
     debug_ts: torch.Tensor | None = None,
+    out2: torch.Tensor | None = None,          # bf16 [rows, >=n] second copy (or the fused-LN operand, see ln_scale)
+    ln_scale: torch.Tensor | None = None,      # f32 [n]: producer mode — out2 = bf16(out * (1 + ln_scale)), ln_stats filled
+    ln_stats: torch.Tensor | None = None,      # f32 [rows, n/32, 2]
+    ln_in_stats: torch.Tensor | None = None,   # f32 [rows, k/32, 2]: consumer mode
+    ln_tab: torch.Tensor | None = None,        # f32 [4, >=n] rows c1_hi, c1_lo, c2_hi, c2_lo
 ) -> torch.Tensor:
-    _need_cuda(a, w, out, bias, resid, gate, row_len, rope)
+    _need_cuda(a, w, out, bias, resid, gate, row_len, rope, out2, ln_scale, ln_stats, ln_in_stats, ln_tab)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
     m = a.shape[0]
@@ -92,5 +97,14 @@ def gemm(
     g.variant = variant
     if debug_ts is not None:
         g.debug_ts = debug_ts.data_ptr()
+    if out2 is not None:
+        assert out2.dtype == torch.bfloat16 and out2.stride(-1) == 1
+        g.out2_bf16, g.ldo2 = out2.data_ptr(), out2.stride(0)
+    if ln_scale is not None:
+        assert ln_scale.dtype == torch.float32 and ln_stats is not None and ln_stats.dtype == torch.float32
+        g.ln_scale, g.ln_stats = ln_scale.data_ptr(), ln_stats.data_ptr()
+    if ln_in_stats is not None:
+        assert ln_in_stats.dtype == torch.float32 and ln_tab is not None and ln_tab.dtype == torch.float32
+        g.ln_in_stats, g.ln_tab, g.ln_tab_ld = ln_in_stats.data_ptr(), ln_tab.data_ptr(), ln_tab.stride(0)
     _lib.check(_lib.load().f5_gemm_bf16(C.byref(g), _stream()))
     return out

@@ -61,3 +61,34 @@ def gather_objects(local: list) -> Optional[list]:
     if rank != 0:
         return None
     return [x for part in out for x in part]
+
+
+def sample_sharded(f5, cond: torch.Tensor, text, duration: torch.Tensor, **kw):
+    """Data-parallel F5TTS.sample over the ranks of the default process group: utterance i of the global batch goes
+    to the rank whose shard_range holds it, every shard pads to the GLOBAL frame count (one int all-reduce — the only
+    communication before the host-side gather), and rank 0 receives the mel outputs in global order (others: None).
+    `cond` (b, n, mel), `text` (b, nt) int tensor or list of str, `duration` (b,) are the GLOBAL batch on every rank;
+    `y0`, if given, is the global noise (b, N, mel)."""
+    rank, ws = world()
+    b = cond.shape[0]
+    mine = shard_range(b, ws, rank)
+    duration = torch.as_tensor(duration).reshape(-1)
+    dev = f5.transformer.device
+    if len(mine) == 0:
+        global_frames(0, device=dev)
+        return gather_objects([])
+    sl = slice(mine.start, mine.stop)
+    text_l = text[sl] if not isinstance(text, list) else text[mine.start:mine.stop]
+    # the frame count sample() will derive for this shard (cfm.py:301-319), then the global maximum
+    if isinstance(text_l, list):
+        text_len = torch.tensor([len(t) for t in text_l])
+    else:
+        text_len = (text_l != -1).sum(dim=-1)
+    lens = torch.maximum(text_len.float(), torch.full((len(mine),), float(cond.shape[1])))
+    n_local = int(torch.clip(torch.maximum(lens + 1, duration[sl].float()), 0, kw.get("max_duration", 4096)).max().item())
+    n_glob = global_frames(n_local, device=dev)
+    y0 = kw.pop("y0", None)
+    if y0 is not None:
+        y0 = y0[sl]
+    out, _ = f5.sample(cond[sl], text_l, duration[sl], y0=y0, pad_frames=n_glob, return_trajectory=False, **kw)
+    return gather_objects([o.cpu() for o in out])

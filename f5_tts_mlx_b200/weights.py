@@ -208,6 +208,63 @@ def convert_upstream_keys(weights: Weights) -> Weights:
 
 
 # ---------------------------------------------------------------------------------------------
+# MLX affine quantisation (cfm.py:451-452, 510-515): `model_v1_{4,8}b.safetensors` store, for every nn.Linear whose
+# input dim is a multiple of 64, `weight` (uint32, `32 // bits` codes per word, code j of a word in bits
+# [j*bits, (j+1)*bits)), `scales` and `biases` (one per group of 64 consecutive input channels):
+#     w[o, i] = scales[o, i // 64] * code[o, i] + biases[o, i // 64]        (mx.dequantize)
+# The B200 path computes in bf16 anyway, so such files are dequantised once at load time (pack time).
+# ---------------------------------------------------------------------------------------------
+MLX_GROUP_SIZE = 64
+
+
+def dequantize_mlx_affine(wq: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, bits: int,
+                          group_size: int = MLX_GROUP_SIZE) -> torch.Tensor:
+    if bits not in (2, 4, 8):
+        raise ValueError(f"unsupported MLX quantisation width: {bits} bits")
+    per_word = 32 // bits
+    words = wq.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF          # uint32 payload, whatever the dtype tag
+    out_f, n_words = words.shape
+    shifts = torch.arange(per_word, dtype=torch.int64) * bits
+    codes = ((words[:, :, None] >> shifts) & ((1 << bits) - 1)).reshape(out_f, n_words * per_word).float()
+    in_f = codes.shape[1]
+    if scales.shape != (out_f, in_f // group_size) or biases.shape != scales.shape:
+        raise ValueError(f"quantised Linear {tuple(wq.shape)}: scales/biases {tuple(scales.shape)} do not match "
+                         f"{out_f} x {in_f // group_size} groups of {group_size}")
+    g = codes.view(out_f, in_f // group_size, group_size)
+    return (g * scales.float()[:, :, None] + biases.float()[:, :, None]).reshape(out_f, in_f)
+
+
+def quantize_mlx_affine(w: torch.Tensor, bits: int, group_size: int = MLX_GROUP_SIZE):
+    """Min/max affine quantiser producing the MLX file layout (used by the tests and by tools that want a `--q`
+    style checkpoint); returns (packed uint32-as-int32 weight, scales, biases)."""
+    out_f, in_f = w.shape
+    assert in_f % group_size == 0
+    g = w.float().view(out_f, in_f // group_size, group_size)
+    lo, hi = g.min(dim=-1).values, g.max(dim=-1).values
+    n_bins = (1 << bits) - 1
+    scales = ((hi - lo) / n_bins).clamp_min(1e-7)
+    codes = torch.round((g - lo[:, :, None]) / scales[:, :, None]).clamp(0, n_bins).to(torch.int64).reshape(out_f, in_f)
+    per_word = 32 // bits
+    shifts = torch.arange(per_word, dtype=torch.int64) * bits
+    words = (codes.view(out_f, in_f // per_word, per_word) << shifts).sum(dim=-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return words, scales, lo
+
+
+def dequantize_mlx_checkpoint(weights: Weights, bits: int, group_size: int = MLX_GROUP_SIZE) -> Weights:
+    """Replaces every (`X.weight` packed, `X.scales`, `X.biases`) triple by the dense fp32 `X.weight`."""
+    out: Weights = {}
+    for k, v in weights.items():
+        if k.endswith(".scales") or k.endswith(".biases"):
+            continue
+        stem = k[: -len(".weight")] if k.endswith(".weight") else None
+        if stem is not None and stem + ".scales" in weights:
+            v = dequantize_mlx_affine(v, weights[stem + ".scales"], weights[stem + ".biases"], bits, group_size)
+        out[k] = v
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # packing
 # ---------------------------------------------------------------------------------------------
 class ConvNextWeightsC(C.Structure):

@@ -50,6 +50,13 @@ long long f5_launch_count(void);
 int f5_struct_sizes(int32_t* out, int32_t n);
 int f5_prof_enable(int on);
 int f5_prof_summary(double* out, int kinds);
+/* In-situ kernel timing inside a captured CUDA graph (bench.py's roofline): install a device buffer of max_slots x 2
+ * uint64; from then on the i-th launched kernel of the tensor-core families (GEMM, attention) gets slot i and writes
+ * [i][0] = min over its CTAs of %globaltimer after the dependency wait, [i][1] = max over CTAs at exit (the caller
+ * presets the columns to UINT64_MAX / 0 before each replay).  f5_prof_graph_meta returns the family (kinds as above)
+ * and the algorithmic flops / bytes of every slot handed out since the install; slots = NULL uninstalls. */
+int f5_prof_graph_begin(void* slots, int32_t max_slots);
+int f5_prof_graph_meta(int32_t* kinds, double* flops, double* bytes, int32_t cap);
 
 /* ------------------------------------------------------------------------------------------ *
  * Dense / implicit-conv GEMM on tcgen05 tensor cores:  out = epilogue(A · W^T)
@@ -101,6 +108,21 @@ typedef struct f5_gemm_args {
   void* debug_ts;         /* NULL, or uint64 [ctas, 10]: per-CTA phase timestamps (globaltimer ns)  */
   const void* prefetch;   /* NULL, or device memory (weights of a later GEMM) to pull into L2       */
   int64_t prefetch_bytes;
+  /* Fused AdaLayerNormZero (dit.py:262-271, 281-290; call sites dit.py:313,321,397) by linearity of the Linear that
+   * consumes the normalised activations:
+   *     Linear(LN(x) * (1 + s) + b) = rstd * ((x * (1 + s)) W^T - mean * c1) + c2,   c1 = (1 + s) W^T,  c2 = b W^T.
+   * Producer side (the GEMM whose fp32 `out` is the residual stream x): with `ln_scale` = s of the NEXT AdaLN,
+   * out2_bf16 receives bf16(out * (1 + s[col])) and ln_stats[row][col / 32] the (mean, M2) of each 32-column chunk
+   * of the finished row (requires out_bf16 == 0, n % 32 == 0).
+   * Consumer side (`a` is such an out2 matrix): with `ln_in_stats` = that statistics array ([rows][k / 32][2]) the
+   * epilogue computes rstd * (acc - mean * c1[col]) + c2[col] + bias[col] before the activation; ln_tab holds 4 rows
+   * of ln_tab_ld floats — c1_hi, c1_lo, c2_hi, c2_lo (the table GEMM runs on a bf16 hi/lo split of (1 + s) and b,
+   * f5_dit_precompute) — already offset to this GEMM's column 0.  gate must be NULL. */
+  const float* ln_scale;
+  float* ln_stats;
+  const float* ln_in_stats;
+  const float* ln_tab;
+  int64_t ln_tab_ld;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
@@ -227,11 +249,23 @@ typedef struct f5_dit_buffers {
   void* qkv_bf16;             /* bf16 [rows, 3D] */
   void* ff_bf16;              /* bf16 [rows, ff_inner] */
   float* v;                   /* fp32 [rows, mel_dim]: DiT output (flow prediction) */
+  /* Fused AdaLN (see f5_gemm_args.ln_*): all three non-NULL selects it, any NULL keeps the separate
+   * f5_ln_modulate launches.  ln_tab_ld = depth*(3D + ff_inner) + 128 (f5_dit_ln_tab_ld). */
+  float* ln_stats;            /* fp32 [rows, D/32, 2]: per-row chunk statistics of the residual stream */
+  float* ln_tab;              /* fp32 [4*n_times, ln_tab_ld]: c1/c2 operand rows per time, columns = per block [qkv 3D | ff1 F], then proj_out */
+  void* ln_prep;              /* bf16 [2*depth+1, 4*n_times, D]: operand rows of the table GEMMs */
+  /* Frame bucketing (plan reuse across utterances of different length): the buffers are sized for `frames` rows per
+   * utterance but only the first valid_len[u] (= the reference's N, cfm.py:319) exist; rows beyond are kept exactly
+   * zero where the reference's zero padding would be seen (the k=31 ConvPositionEmbedding input, dit.py:45) and are
+   * masked as attention keys, so rows < N equal the unpadded computation.  NULL = all `frames` rows are real. */
+  const int32_t* valid_len;   /* int32 [rows/frames], every entry the same N <= frames, or NULL */
 } f5_dit_buffers;
 
 /* step-invariant work, once per sample(): text embedding (dit.py:196-229), hoisted conditioning
  * projection, TimestepEmbedding + every AdaLN linear for all n_times (dit.py:73-82,267,286). */
 int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* b, void* stream);
+/* row length (floats) of f5_dit_buffers.ln_tab for this model */
+int64_t f5_dit_ln_tab_ld(const f5_dit_weights* w);
 /* one DiT evaluation (dit.py:374-401) at tvals[time_index] on the state in b->y_bf16 -> b->v */
 int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, int32_t time_index, void* stream);
 

@@ -45,8 +45,10 @@ Weights = Dict[str, Tensor]
 class Precision:
     """fp32 everywhere (the reference), or bf16-rounded tensor-core operands (the CUDA path)."""
 
-    def __init__(self, emulate_bf16: bool = False):
+    def __init__(self, emulate_bf16: bool = False, ln_by_linearity: bool = False):
         self.emulate_bf16 = emulate_bf16
+        # rounding points of the CUDA path's fused AdaLN (see adaln_linear below); only meaningful with emulate_bf16
+        self.ln_by_linearity = ln_by_linearity
 
     def op(self, x: Tensor) -> Tensor:
         return x.bfloat16().float() if self.emulate_bf16 else x
@@ -58,6 +60,26 @@ FP32 = Precision(False)
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor], prec: Precision = FP32) -> Tensor:
     """mlx.nn.Linear: x @ W^T + b."""
     return F.linear(prec.op(x), prec.op(w), b)
+
+
+def adaln_linear(x: Tensor, scale: Tensor, shift: Tensor, w: Tensor, b: Optional[Tensor], prec: Precision = FP32,
+                 eps: float = 1e-6) -> Tensor:
+    """Linear(LayerNorm(x) * (1 + scale) + shift) — dit.py:270 + the Linear that consumes it (dit.py:136-143, 94,
+    398).  fp32: exactly that.  With `prec.ln_by_linearity` it applies the CUDA path's rounding points: the
+    producer GEMM's epilogue stores bf16(x * (1 + scale)) and per-row (mean, M2); the consumer GEMM multiplies that
+    operand and finishes the LayerNorm in its epilogue by linearity,
+        out = rstd * (x~ @ W^T - mean * c1) + c2,   c1 = (1 + scale) @ W^T,  c2 = shift @ W^T + b   (fp32 tables)."""
+    d = x.shape[-1]
+    if not (prec.emulate_bf16 and prec.ln_by_linearity):
+        norm = F.layer_norm(x, (d,), eps=eps) * (1 + scale[:, None]) + shift[:, None]
+        return linear(norm, w, b, prec)
+    mu = x.mean(dim=-1, keepdim=True)
+    rstd = torch.rsqrt(x.var(dim=-1, unbiased=False, keepdim=True) + eps)
+    wb = prec.op(w)
+    xt = prec.op(x * (1 + scale[:, None]))
+    c1 = F.linear(1 + scale, wb)[:, None]
+    c2 = F.linear(shift, wb, b)[:, None]
+    return rstd * (F.linear(xt, wb) - mu * c1) + c2
 
 
 def conv1d_nlc(x: Tensor, w_mlx: Tensor, b: Optional[Tensor], padding: int, groups: int,
@@ -302,13 +324,17 @@ def input_embedding(x: Tensor, cond: Tensor, text_embed: Tensor, drop_audio_cond
 
 
 def attention(x: Tensor, mask: Optional[Tensor], rope: Tensor, W: Weights, pfx: str, heads: int,
-              prec: Precision = FP32) -> Tensor:
+              prec: Precision = FP32, adaln: Optional[Tuple[Tensor, Tensor]] = None) -> Tensor:
     """dit.py:126-175.  `mask` (b, n) bool = key-padding mask with the INTENDED semantics of
     dit.py:161-166 (the reference's `.expand` call is not an mx.array method)."""
     b, n, _ = x.shape
-    q = linear(x, W[pfx + "to_q.weight"], W[pfx + "to_q.bias"], prec)
-    k = linear(x, W[pfx + "to_k.weight"], W[pfx + "to_k.bias"], prec)
-    v = linear(x, W[pfx + "to_v.weight"], W[pfx + "to_v.bias"], prec)
+    if adaln is not None:   # x is the un-normalised stream; AdaLayerNormZero (dit.py:270) feeds to_q/k/v (dit.py:313-316)
+        lin = lambda w, bb: adaln_linear(x, adaln[0], adaln[1], w, bb, prec)
+    else:
+        lin = lambda w, bb: linear(x, w, bb, prec)
+    q = lin(W[pfx + "to_q.weight"], W[pfx + "to_q.bias"])
+    k = lin(W[pfx + "to_k.weight"], W[pfx + "to_k.bias"])
+    v = lin(W[pfx + "to_v.weight"], W[pfx + "to_v.bias"])
     q = q.reshape(b, n, heads, -1).permute(0, 2, 1, 3)
     k = k.reshape(b, n, heads, -1).permute(0, 2, 1, 3)
     v = v.reshape(b, n, heads, -1).permute(0, 2, 1, 3)
@@ -341,11 +367,10 @@ def dit_block(x: Tensor, t: Tensor, mask: Optional[Tensor], rope: Tensor, W: Wei
     dim = cfg.dim
     emb = linear(F.silu(t), W[p + "attn_norm.linear.weight"], W[p + "attn_norm.linear.bias"], prec)
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
-    norm = F.layer_norm(x, (dim,), eps=1e-6) * (1 + scale_msa[:, None]) + shift_msa[:, None]
-    attn_out = attention(norm, mask, rope, W, p + "attn.", cfg.heads, prec)
+    attn_out = attention(x, mask, rope, W, p + "attn.", cfg.heads, prec, adaln=(scale_msa, shift_msa))
     x = x + gate_msa[:, None] * attn_out
-    norm = F.layer_norm(x, (dim,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
-    h = linear(norm, W[p + "ff.ff.layers.0.layers.0.weight"], W[p + "ff.ff.layers.0.layers.0.bias"], prec)
+    h = adaln_linear(x, scale_mlp, shift_mlp, W[p + "ff.ff.layers.0.layers.0.weight"],
+                     W[p + "ff.ff.layers.0.layers.0.bias"], prec)
     h = F.gelu(h, approximate="tanh")
     ff = linear(h, W[p + "ff.ff.layers.2.weight"], W[p + "ff.ff.layers.2.bias"], prec)
     return x + gate_mlp[:, None] * ff
@@ -366,8 +391,7 @@ def dit_forward(x: Tensor, cond: Tensor, text: Tensor, time: Tensor, drop_audio_
         x = dit_block(x, t, mask, rope, W, i, cfg, prec)                   # :395-396
     emb = linear(F.silu(t), W["transformer.norm_out.linear.weight"], W["transformer.norm_out.linear.bias"], prec)
     scale, shift = emb.chunk(2, dim=1)                                     # dit.py:287 (scale FIRST)
-    x = F.layer_norm(x, (cfg.dim,), eps=1e-6) * (1 + scale[:, None]) + shift[:, None]
-    return linear(x, W["transformer.proj_out.weight"], W["transformer.proj_out.bias"], prec)
+    return adaln_linear(x, scale, shift, W["transformer.proj_out.weight"], W["transformer.proj_out.bias"], prec)
 
 
 # ---------------------------------------------------------------------------------------------

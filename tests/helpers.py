@@ -14,11 +14,11 @@ def rel(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
 
 
-def make_dit(cfg, W, device="cuda"):
+def make_dit(cfg, W, device="cuda", fused_adaln=True):
     from f5_tts_mlx_b200 import DiT
     return DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
                text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers,
-               device=device).load_weights(W)
+               device=device, fused_adaln=fused_adaln).load_weights(W)
 
 
 def synth_audio(length: int, seed: int = 0) -> torch.Tensor:

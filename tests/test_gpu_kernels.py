@@ -162,3 +162,66 @@ def test_dwconv7_ln_and_grn():
     Gx = hf.pow(2).sum(1, keepdim=True).sqrt()
     ref = gamma * (hf * (Gx / (Gx.mean(-1, keepdim=True) + 1e-6))) + beta + hf
     assert rel(out, ref) < 4e-3
+
+
+# ---------------- fused AdaLayerNormZero (f5_gemm_args.ln_*) ----------------
+def _ln_tab(scale, shift, w):
+    """What f5_dit_precompute's table GEMM produces for one time: rows c1_hi, c1_lo, c2_hi, c2_lo from the bf16
+    hi/lo split of (1 + scale) and shift against the bf16 weight."""
+    a = 1 + scale
+    ah = a.bfloat16().float(); al = (a - ah).bfloat16().float()
+    bh = shift.bfloat16().float(); bl = (shift - bh).bfloat16().float()
+    return torch.stack([ah @ w.float().T, al @ w.float().T, bh @ w.float().T, bl @ w.float().T]).contiguous()
+
+
+@pytest.mark.parametrize("M,D,K,variant,tile", [(1874, 1024, 1024, 1, 0), (1874, 1024, 2048, 1, 0), (300, 512, 512, 1, 64),
+                                                (700, 1024, 1024, 2, 256), (40000, 1024, 2048, 0, 0)])
+def test_gemm_fused_ln_producer(M, D, K, variant, tile):
+    """out-proj / FF2 shape: x = resid + gate * (a W^T + bias) in fp32, plus the bf16 operand x * (1 + s) and the
+    per-row chunk statistics (mean, M2 per 32 columns) of x — all three against fp32 torch."""
+    from f5_tts_mlx_b200 import ops
+    a = rnd(M, K).bfloat16(); w = rnd(D, K, scale=K ** -0.5).bfloat16(); bias = rnd(D)
+    gate = rnd(1, D); x = rnd(M, D) * 2 + 0.3; x0 = x.clone(); s = rnd(D, seed=5) * 0.3
+    xt = torch.full((M, D), float("nan"), device=dev, dtype=torch.bfloat16)
+    stats = torch.full((M, D // 32, 2), float("nan"), device=dev)
+    ops.gemm(a, w, x, bias=bias, resid=x, gate=gate[0], out2=xt, ln_scale=s, ln_stats=stats, variant=variant, tile_n=tile)
+    ref = x0 + gate * (a.float() @ w.float().T + bias)
+    assert rel(x, ref) < 1e-5
+    assert rel(xt, ref * (1 + s)) < 4e-3
+    chunks = ref.view(M, D // 32, 32)
+    assert (stats[..., 0] - chunks.mean(-1)).abs().max().item() < 1e-4
+    m2 = ((chunks - chunks.mean(-1, keepdim=True)) ** 2).sum(-1)
+    assert rel(stats[..., 1], m2) < 1e-4
+
+
+@pytest.mark.parametrize("M,D,N,act,rope", [(1874, 1024, 3072, 0, True), (1874, 1024, 2048, 1, False), (937, 1024, 100, 0, False),
+                                            (300, 512, 1536, 0, True), (40000, 1024, 2048, 1, False)])
+def test_gemm_fused_ln_consumer(M, D, N, act, rope):
+    """QKV / FF1 / proj_out shape: Linear(LayerNorm(x) * (1 + s) + b) from the producer's operand x~ = bf16(x (1+s)),
+    its chunk statistics and the c1/c2 table, against fp32 torch on the un-normalised x."""
+    from f5_tts_mlx_b200 import ops
+    from f5_tts_mlx_b200.dit import rope_table
+    x = rnd(M, D) * 1.7 + 0.4
+    s = rnd(D, seed=7) * 0.3; b = rnd(D, seed=8) * 0.5
+    w = rnd(N, D, scale=D ** -0.5).bfloat16(); bias = rnd(N)
+    xt = (x * (1 + s)).bfloat16()
+    chunks = x.view(M, D // 32, 32)
+    stats = torch.stack([chunks.mean(-1), ((chunks - chunks.mean(-1, keepdim=True)) ** 2).sum(-1)], dim=-1).contiguous()
+    tab = _ln_tab(s, b, w)
+    f32 = N == 100
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    kw = {}
+    if rope:
+        kw = dict(rope=rope_table(M).to(dev), rope_cols=2 * N // 3, q_scale=0.125, q_cols=N // 3, rows_per_batch=M, num_batches=1)
+    ops.gemm(xt, w, out, bias=bias, act=act, ln_in_stats=stats, ln_tab=tab, **kw)
+    ref = (F.layer_norm(x, (D,), eps=1e-6) * (1 + s) + b) @ w.float().T + bias
+    if act == 1:
+        ref = F.gelu(ref, approximate="tanh")
+    if rope:
+        r = ref.view(M, N // 64, 32, 2)
+        c, sn = kw["rope"][:, None, :, 0], kw["rope"][:, None, :, 1]
+        rot = torch.stack([r[..., 0] * c - r[..., 1] * sn, r[..., 1] * c + r[..., 0] * sn], dim=-1)
+        r2 = r.clone(); r2[:, : kw["rope_cols"] // 64] = rot[:, : kw["rope_cols"] // 64]
+        ref = r2.reshape(M, N).clone(); ref[:, : N // 3] *= 0.125
+    # the operand is bf16(x (1+s)): its rounding error is relative to |x| (not |x - mean|); mean/std here is 0.24
+    assert rel(out, ref) < 6e-3

@@ -197,7 +197,49 @@ def test_from_pretrained_local_directory_roundtrip(tmp_path):
     save_file(inv, str(tmp_path / "model_v1.safetensors"))
     f5b = PT.from_pretrained(F5TTS, str(tmp_path), device="cpu")
     assert torch.equal(f5b.transformer.packed.buffer, f5.transformer.packed.buffer)
-    with pytest.raises(NotImplementedError):
-        PT.from_pretrained(F5TTS, str(tmp_path), quantization_bits=4)
     with pytest.raises(ValueError):
         PT.from_pretrained(F5TTS, str(tmp_path / "missing"))
+    # MLX affine 4/8-bit checkpoints (cfm.py:450-453, 510-517; generate.py --q): model_v1_{bits}b.safetensors with
+    # (weight uint32, scales, biases) per Linear whose input dim is a multiple of 64 -> dequantised at pack time
+    from f5_tts_mlx_b200.weights import dequantize_mlx_affine, dequantize_mlx_checkpoint, quantize_mlx_affine
+    for bits in (8, 4):
+        q = {}
+        for k, v in W.items():
+            if "inv_freq" in k:
+                continue
+            if k.endswith(".weight") and v.ndim == 2 and v.shape[1] % 64 == 0 and not k.endswith("text_embed.text_embed.weight"):
+                wq, sc, bi = quantize_mlx_affine(v, bits)
+                q[k], q[k[:-7] + ".scales"], q[k[:-7] + ".biases"] = wq, sc, bi
+            else:
+                q[k] = v.contiguous()
+        save_file(q, str(tmp_path / f"model_v1_{bits}b.safetensors"))
+        f5q = PT.from_pretrained(F5TTS, str(tmp_path), quantization_bits=bits, device="cpu")
+        name = "transformer.transformer_blocks.5.ff.ff.layers.0.layers.0.weight"
+        dense = dequantize_mlx_checkpoint(q, bits)[name]
+        assert torch.equal(f5q.transformer.packed.view("blk5.ff1_w").float(), dense.bfloat16().float())
+        step = (W[name].view(W[name].shape[0], -1, 64).amax(-1) - W[name].view(W[name].shape[0], -1, 64).amin(-1)) / (2 ** bits - 1)
+        assert ((dense - W[name]).abs().view(W[name].shape[0], -1, 64).amax(-1) <= 0.5001 * step + 1e-7).all()
+    with pytest.raises(ValueError):
+        PT.from_pretrained(F5TTS, str(tmp_path), quantization_bits=3)
+    # the vocoder is mandatory like in the reference (cfm.py:446): no checkpoint anywhere -> loud failure, unless
+    # the caller opts out explicitly
+    (tmp_path / "vocos.safetensors").unlink()
+    with pytest.raises(FileNotFoundError):
+        PT.from_pretrained(F5TTS, str(tmp_path), device="cpu")
+    assert PT.from_pretrained(F5TTS, str(tmp_path), device="cpu", vocoder=False)._vocoder is None
+
+
+def test_mlx_affine_dequantisation_known_answer():
+    """mx.dequantize layout: code j of a uint32 word sits in bits [j*bits, (j+1)*bits); one (scale, bias) per 64 inputs."""
+    from f5_tts_mlx_b200.weights import dequantize_mlx_affine
+    codes = (torch.arange(128) % 16).view(1, 128)
+    words4 = (codes.view(1, 16, 8).long() << (torch.arange(8) * 4)).sum(-1)
+    words4 = torch.where(words4 >= 2 ** 31, words4 - 2 ** 32, words4).to(torch.int32)
+    sc, bi = torch.tensor([[0.5, 2.0]]), torch.tensor([[-1.0, 3.0]])
+    w = dequantize_mlx_affine(words4, sc, bi, 4)
+    exp = torch.cat([codes[0, :64] * 0.5 - 1.0, codes[0, 64:] * 2.0 + 3.0])[None]
+    assert torch.equal(w, exp)
+    codes8 = (torch.arange(64) * 3 + 7).view(1, 64)
+    words8 = (codes8.view(1, 16, 4).long() << (torch.arange(4) * 8)).sum(-1)
+    words8 = torch.where(words8 >= 2 ** 31, words8 - 2 ** 32, words8).to(torch.int32)
+    assert torch.equal(dequantize_mlx_affine(words8, torch.tensor([[0.25]]), torch.tensor([[1.0]]), 8), codes8 * 0.25 + 1.0)

@@ -160,6 +160,7 @@ def test_generate_host_logic_matches_reference_generate(golden_dir, tmp_path):
 
     class Rec:
         _duration_predictor = None
+        _vocoder = staticmethod(lambda mel: mel)      # generate() refuses a model without a vocoder
 
         class transformer:
             device = torch.device("cpu")
