@@ -81,7 +81,7 @@ extern "C" int f5_dit_precompute(const f5_dit_weights* w, const f5_dit_buffers* 
       g.bias = cw.pw1_b; g.act = F5_ACT_GELU_ERF;
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
-    if (int e = launch_grn(b->text_h, b->text_g, b->grn_nx, cw.grn_gamma, cw.grn_beta, BU, N, Ci, st))
+    if (int e = launch_grn(b->text_h, b->text_g, b->grn_nx, cw.grn_gamma, cw.grn_beta, BU, N, Ci, st, b->valid_len))
       return e;
     {  // pwconv2 + residual, then the re-mask of dit.py:225 (masked rows have a zero residual)
       f5_gemm_args g = gemm_base(b->text_g, Ci, cw.pw2_w, Ci, R, C, Ci, b->text_x, C, false);

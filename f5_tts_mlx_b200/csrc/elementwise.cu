@@ -67,13 +67,13 @@ int launch_dwconv7_ln(const float* x, void* y, int B, int N, int C, const float*
 }
 
 int launch_grn(const void* h, void* y, float* nx_scratch, const float* gamma, const float* beta,
-               int B, int N, int C, cudaStream_t st) {
+               int B, int N, int C, cudaStream_t st, const int* valid_len) {
   ProfScope ps(PROF_OTHER, 0.0, 0.0, st);
   F5_REQUIRE(h && y && nx_scratch && gamma && beta, "grn: null pointer");
   F5_REQUIRE(C % 4 == 0, "grn: C %% 4");
   const int nblk = cdiv(N, kGrnRowsPerBlock);
   F5_CHECK_CUDA(launch_kernel(grn_sumsq_kernel, dim3(nblk, B), dim3(256), 0, st,
-                              reinterpret_cast<const __nv_bfloat16*>(h), nx_scratch, N, C, nblk));
+                              reinterpret_cast<const __nv_bfloat16*>(h), nx_scratch, N, C, nblk, valid_len));
   F5_CHECK_CUDA(launch_kernel(grn_finalize_kernel, dim3(B), dim3(256), 0, st, nx_scratch, C, nblk));
   const long long total4 = (long long)B * N * C / 4;
   F5_CHECK_CUDA(launch_kernel(grn_apply_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st,

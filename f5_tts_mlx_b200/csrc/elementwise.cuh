@@ -175,12 +175,14 @@ constexpr int kGrnRowsPerBlock = 32;
 
 __global__ void __launch_bounds__(256)
 grn_sumsq_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ scratch, int N, int C,
-                 int nblk) {
+                 int nblk, const int* __restrict__ valid_len) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * kGrnRowsPerBlock;
-  const int r1 = min(N, r0 + kGrnRowsPerBlock);
+  // frame bucketing: rows >= valid_len[b] do not exist in the reference's (b, N, C) tensor — they must not enter the norm
+  const int nv = valid_len != nullptr ? min(N, valid_len[b]) : N;
+  const int r1 = min(nv, r0 + kGrnRowsPerBlock);
   float* part = scratch + ((size_t)b * (1 + nblk) + 1 + blockIdx.x) * C;
   for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;

@@ -8,8 +8,8 @@
 namespace f5 {
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       dim3 grid, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                       const GemmParams& p, dim3 grid, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages>;
   auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
   static SmemAttrOnce once;  // per instantiation
@@ -21,17 +21,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                stream);
   GemmParams q = p;
   q.prof = ps.slot;
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, q));
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, to, to2, q));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN, int kStages>
 static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta,
-                        const CUtensorMap& tb, const GemmParams& p, dim3 grid,
-                        cudaStream_t stream) {
+                        const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const GemmParams& p,
+                        dim3 grid, cudaStream_t stream) {
 #define F5_CASE(A, O, R) \
-  if (act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R>(ta, tb, p, grid, stream);
+  if (act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R>(ta, tb, to, to2, p, grid, stream);
   F5_CASE(ACT_NONE, true, true)
   F5_CASE(ACT_NONE, true, false)
   F5_CASE(ACT_NONE, false, false)
@@ -45,8 +45,8 @@ static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta
 }
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                        int n_tiles, int total_tiles, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                        const GemmParams& p, int n_tiles, int total_tiles, cudaStream_t stream) {
   using S = Gemm2Smem<BN, kStages, Gemm2Lno<BN, OUT_BF16>::value>;
   auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
   static SmemAttrOnce once;
@@ -60,17 +60,17 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
                stream);
   GemmParams q = p;
   q.prof = ps.slot;
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), S::kTotal, stream, ta, tb, q, n_tiles, total_tiles));
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(2 * clusters), dim3(384), S::kTotal, stream, ta, tb, to, to2, q, n_tiles, total_tiles));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN, int kStages>
 static int dispatch_epi2(int act, bool out_bf16, bool rope, const CUtensorMap& ta,
-                         const CUtensorMap& tb, const GemmParams& p, int n_tiles, int total_tiles,
-                         cudaStream_t stream) {
+                         const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const GemmParams& p,
+                         int n_tiles, int total_tiles, cudaStream_t stream) {
 #define F5_CASE(A, O, R) \
-  if (act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R>(ta, tb, p, n_tiles, total_tiles, stream);
+  if (act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R>(ta, tb, to, to2, p, n_tiles, total_tiles, stream);
   F5_CASE(ACT_NONE, true, true)
   F5_CASE(ACT_NONE, true, false)
   F5_CASE(ACT_NONE, false, false)
@@ -136,6 +136,20 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   if (a->resid) F5_REQUIRE(a->ldr % 4 == 0, "f5_gemm_bf16: ldr not multiple of 4");
   if (a->gate) F5_REQUIRE(a->gate_ld % 4 == 0, "f5_gemm_bf16: gate_ld not multiple of 4");
 
+  // output tensor maps (TMA stores of the epilogue): (cols, rows per utterance, utterances) when tiles never straddle
+  // utterances, else (cols, m, 1)
+  CUtensorMap to, to2;
+  {
+    const uint64_t orows = batched ? (uint64_t)rpb : (uint64_t)a->m, obat = batched ? (uint64_t)nb : 1;
+    if (int e = make_tmap_out(&to, a->out, a->out_bf16 ? 2 : 4, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo)) return e;
+    if (a->out2_bf16) {
+      F5_REQUIRE(!a->out_bf16, "f5_gemm_bf16: out2_bf16 needs an fp32 out");
+      if (int e = make_tmap_out(&to2, a->out2_bf16, 2, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo2)) return e;
+    } else {
+      to2 = to;
+    }
+  }
+
   int variant = a->variant;
   {
     static int forced = -1;   // debugging aid: F5_GEMM_VARIANT=1|2 overrides the automatic choice
@@ -155,14 +169,15 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     const int sms = sm_count();
     variant = (a->n >= 128 && (pair_tiles >= sms || (pair_tiles >= sms / 2 && a->n >= 3072))) ? 2 : 1;
   }
-  if (variant == 2 && a->ln_scale && a->tile_n != 0 && a->tile_n != 256) variant = 1;   // pair kernel: LN producer mode with 256-wide tiles only
-  if (variant == 2 && a->ln_scale && !(a->n % 256 == 0 || a->n >= 1024)) variant = 1;
+  // pair kernel: a second output (out2 / fused-LN producer mode) with 256-wide tiles only
+  if (variant == 2 && a->out2_bf16 && a->tile_n != 0 && a->tile_n != 256) variant = 1;
+  if (variant == 2 && a->out2_bf16 && !(a->n % 256 == 0 || a->n >= 1024)) variant = 1;
   if (variant == 2) {
     int bn2 = a->tile_n;
     if (bn2 == 0) bn2 = (a->n % 256 == 0 || a->n >= 1024) ? 256 : 128;
     // wide outputs on few row tiles (QKV at batch 1: 8 x 12 tiles of 256 columns on 74 SM pairs = two
     // rounds, the second 30 % full): 192-column tiles give 8 x 16 smaller tiles
-    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0 && !a->ln_scale) {
+    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0 && !a->out2_bf16) {
       const int t256 = cdiv(a->m, 256) * cdiv(a->n, 256), t192 = cdiv(a->m, 256) * cdiv(a->n, 192);
       const int pairs = sm_count() / 2;
       const double c256 = (double)cdiv(t256, pairs) * 256, c192 = (double)cdiv(t192, pairs) * 192;
@@ -208,10 +223,10 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     cudaStream_t stream2 = reinterpret_cast<cudaStream_t>(stream_);
     const bool rope2 = a->rope != nullptr;
     if (bn2 == 192)
-      return dispatch_epi2<192, 5>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+      return dispatch_epi2<192, 5>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, to, to2, p2, n_tiles, n_tiles * m_tiles, stream2);
     if (bn2 == 256)
-      return dispatch_epi2<256, 4>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
-    return dispatch_epi2<128, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, p2, n_tiles, n_tiles * m_tiles, stream2);
+      return dispatch_epi2<256, 4>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, to, to2, p2, n_tiles, n_tiles * m_tiles, stream2);
+    return dispatch_epi2<128, 6>(a->act, a->out_bf16 != 0, rope2, ta2, tb2, to, to2, p2, n_tiles, n_tiles * m_tiles, stream2);
   }
 
   int bn = a->tile_n;
@@ -275,7 +290,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   // grids that fit in one wave leave one CTA per SM anyway: spend the whole smem on a 6-stage ring
   // (192 KB in flight per SM instead of 96 KB) to cover the L2/HBM latency of the operand stream
   if (bn == 128 && (long long)grid.x * grid.y <= sm_count())
-    return dispatch_epi<128, 6>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
-  if (bn == 128) return dispatch_epi<128, 3>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
-  return dispatch_epi<64, 4>(a->act, a->out_bf16 != 0, rope, ta, tb, p, grid, stream);
+    return dispatch_epi<128, 6>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
+  if (bn == 128) return dispatch_epi<128, 3>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
+  return dispatch_epi<64, 4>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
 }

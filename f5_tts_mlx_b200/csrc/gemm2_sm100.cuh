@@ -113,7 +113,8 @@ struct Gemm2Lno {
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
-                     const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
+                     const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
+                     const __grid_constant__ CUtensorMap tma_out2, const GemmParams p,
                      const int n_tiles, const int total_tiles) {
   constexpr bool LNO = Gemm2Lno<BN, OUT_BF16>::value;
   using S = Gemm2Smem<BN, kStages, LNO>;
@@ -139,6 +140,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_out);
+    if (p.out2 != nullptr) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -173,7 +176,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (threadIdx.x == 0) { ts_mark(p, blockIdx.x, 2); prof_stamp_begin(p.prof); }
 
   // register hand-over (384 threads cap every thread at 168): warps 0-3 need few, the epilogue warps hold a
-  // row's RoPE table, residual and accumulator chunk.  128 x 40 + 256 x 232 <= 64 K registers.
+  // row's RoPE table, residual and accumulator chunk.  128 x 40 + 256 x 232 = 64 512 = exactly the 384 x 168 registers
+  // the CTA owns: a larger small budget (tried: 48) makes setmaxnreg.inc wait forever — the kernel hangs.
   // (setmaxnreg must sit INSIDE the role branches, or ptxas applies the small budget to everything.)
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
@@ -304,13 +308,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.buf2 = LNO ? smem + S::kStage2Offset + grp * 8192 : nullptr;
       stg.buf2_par = 0;
       stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
+      stg.map_out = &tma_out;
+      stg.map_out2 = &tma_out2;
       if (pair_tiles_per_batch > 0) {
-        const int m0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
-        stg.row0 = (long long)b_idx_tile * p.rows_per_batch + m0;
-        stg.rows_valid = min(128, p.rows_per_batch - m0);
+        stg.c1 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
+        stg.c2 = b_idx_tile;
       } else {
-        stg.row0 = (long long)m_tile * 256 + (int)rank * 128;
-        stg.rows_valid = min(128, p.M - (int)stg.row0);
+        stg.c1 = m_tile * 256 + (int)rank * 128;
+        stg.c2 = 0;
       }
       epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
                                               gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg, grp, 2,
@@ -319,6 +324,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
     }
+    if (et == 0) tma_store_wait<0>();   // this group's TMA stores have landed before the CTA retires
     if (warp == 4 && lane == 0) ts_mark(p, blockIdx.x, 8);
   }
 

@@ -169,31 +169,38 @@ __device__ __forceinline__ void epi_load_resid(const GemmParams& p, int row, int
   }
 }
 
-// Coalesced stores: a thread owns a ROW, so its 16-byte stores land in 32 different rows per warp
-// instruction (half-sector writes 4 KB apart — measured 5-6 us per 128x128 fp32 tile in situ).
-// Instead every chunk (128 rows x 32 columns) is written to a swizzled shared-memory buffer and
-// then stored cooperatively, 8 (fp32) or 4 (bf16) consecutive lanes covering one row segment, i.e.
-// full 128 B / 64 B runs.  Two buffers alternate, one named barrier (128 epilogue threads) per chunk.
+// Stores: a thread owns a ROW, so direct 16-byte stores would land in 32 different rows per warp instruction
+// (half-sector writes 4 KB apart — measured 5-6 us per 128x128 fp32 tile in situ), and even when re-read from a
+// staging buffer and stored cooperatively the LSU path moved only ~20 B/clk per SM (r02 in-situ: 64 KB per CTA in
+// ~2.5 us, +1.5 us for 32 KB more).  So every chunk (128 rows x 32 columns) is written to shared memory in the
+// layout of a swizzled TMA box (fp32: 128-byte rows, SWIZZLE_128B; bf16: 64-byte rows, SWIZZLE_64B — the XOR patterns
+// below are exactly those) and ONE thread hands it to the TMA unit (cp.async.bulk.tensor store), which also clips
+// rows / columns outside the matrix.  Two staging buffers alternate; per chunk one named barrier (128 threads).
 struct EpiStage {
-  uint8_t* buf;            // 2 x 16 KB, or nullptr: direct per-thread stores
-  int et;                  // epilogue thread 0..127
+  uint8_t* buf;            // 2 x 16 KB staging of this group (1024-byte aligned)
+  uint8_t* buf2;           // staging of the second (bf16) output: 2 x 8 KB (buf2_par = 8192) or 1 x 8 KB (buf2_par = 0)
+  int buf2_par;
+  int et;                  // epilogue thread 0..127 of the group; thread 0 issues the TMA stores
   int r;                   // this thread's row inside the tile
-  long long row0;          // global row of tile row 0
-  int rows_valid;          // rows of the tile that exist
   int bar_id;              // named barrier of this group of 4 epilogue warps (1 + group)
   int probe_cta;           // debug (F5_EPI_PROBE builds): linear CTA id for sub-step stamps
-  // fused-LN producer mode: staging of the bf16 copy (8 KB per chunk); buf2_par = 8192 when two buffers alternate,
-  // 0 when there is room for one only (then a second barrier per chunk guards its reuse)
-  uint8_t* buf2;
-  int buf2_par;
+  const CUtensorMap* map_out;   // (cols, rows per utterance, utterances) of `out` / `out2`
+  const CUtensorMap* map_out2;
+  int c1, c2;              // tensor-map coordinates of tile row 0: row inside the utterance, utterance
   float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics
 };
 
-// `w2` (fused-LN producer mode, fp32 output only): the chunk's bf16 copy, 4 x uint4 per row, stored to p.out2
+// `w2`: the chunk's second output (bf16, 4 x uint4 per row) or nullptr
 template <bool OUT_BF16>
-__device__ __forceinline__ void epi_store_staged(const float (&v)[32], const EpiStage& st, int par,
-                                                 const GemmParams& p, int col0, const uint4* w2 = nullptr) {
+__device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiStage& st, int par, int col0,
+                                              const uint4* w2 = nullptr) {
   uint8_t* buf = st.buf + par * 16384;
+  uint8_t* buf2 = st.buf2 + par * st.buf2_par;
+  if (w2 != nullptr && st.buf2_par == 0) {
+    // one staging buffer for the second output: the previous chunk's store must have read it
+    if (st.et == 0) tma_store_wait_read<0>();
+    asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
+  }
   if (OUT_BF16) {
     uint8_t* mine = buf + st.r * 64;
     const int sw = (st.r >> 1) & 3;
@@ -202,53 +209,28 @@ __device__ __forceinline__ void epi_store_staged(const float (&v)[32], const Epi
       *reinterpret_cast<uint4*>(mine + ((j ^ sw) * 16)) =
           make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-    asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const int q = st.et & 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = i * 32 + (st.et >> 2);
-      if (row < st.rows_valid && col0 + q * 8 < p.N) {
-        const uint4 w = *reinterpret_cast<const uint4*>(buf + row * 64 + ((q ^ ((row >> 1) & 3)) * 16));
-        *reinterpret_cast<uint4*>(out + (size_t)(st.row0 + row) * p.ldo + col0 + q * 8) = w;
-      }
-    }
   } else {
     uint8_t* mine = buf + st.r * 128;
     const int sw = st.r & 7;
-    uint8_t* buf2 = st.buf2 + par * st.buf2_par;
-    if (w2 != nullptr) {
-      if (st.buf2_par == 0) asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");   // previous chunk's readers done
-      uint8_t* mine2 = buf2 + st.r * 64;
-      const int sw2 = (st.r >> 1) & 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
-    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(mine + ((j ^ sw) * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
-    float* out = reinterpret_cast<float*>(p.out);
-    const int q = st.et & 7;
+  }
+  if (w2 != nullptr) {
+    uint8_t* mine2 = buf2 + st.r * 64;
+    const int sw2 = (st.r >> 1) & 3;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = i * 16 + (st.et >> 3);
-      if (row < st.rows_valid && col0 + q * 4 < p.N) {
-        const float4 w = *reinterpret_cast<const float4*>(buf + row * 128 + ((q ^ (row & 7)) * 16));
-        *reinterpret_cast<float4*>(out + (size_t)(st.row0 + row) * p.ldo + col0 + q * 4) = w;
-      }
-    }
-    if (w2 != nullptr) {
-      const int q2 = st.et & 3;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = i * 32 + (st.et >> 2);
-        if (row < st.rows_valid && col0 + q2 * 8 < p.N) {
-          const uint4 w = *reinterpret_cast<const uint4*>(buf2 + row * 64 + ((q2 ^ ((row >> 1) & 3)) * 16));
-          *reinterpret_cast<uint4*>(p.out2 + (size_t)(st.row0 + row) * p.ldo2 + col0 + q2 * 8) = w;
-        }
-      }
-    }
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
+  }
+  fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA unit
+  // the OTHER staging buffer is rewritten by the next chunk: every store issued so far must have read its source
+  // (the previous chunk's store was issued a whole chunk of work ago)
+  if (st.et == 0) tma_store_wait_read<0>();
+  asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
+  if (st.et == 0) {
+    tma_store_3d(st.map_out, buf, col0, st.c1, st.c2);
+    if (w2 != nullptr) tma_store_3d(st.map_out2, buf2, col0, st.c1, st.c2);
+    tma_store_commit();
   }
 }
 
@@ -329,17 +311,19 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
     v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
   }
   if constexpr (!OUT_BF16) {
-    if (p.ln_scale != nullptr && st.buf != nullptr) {
-      // fused-LN producer: statistics of this 32-column chunk of the finished residual-stream row, and the bf16
-      // operand x * (1 + scale) of the GEMM that consumes LN(x)
-      float sum = 0.f;
+    if (p.out2 != nullptr && scale_s != nullptr) {
+      // second output: bf16(v * scale) — the fused-LN operand x * (1 + s) of the GEMM that consumes LN(x) (scale_s = 1
+      // when no ln_scale is given: a plain bf16 copy); with ln_stats also the chunk statistics of the finished row
+      if (p.ln_stats != nullptr) {
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sum += v[j];
-      const float mean = sum * (1.f / 32.f);
-      float m2 = 0.f;
+        for (int j = 0; j < 32; ++j) sum += v[j];
+        const float mean = sum * (1.f / 32.f);
+        float m2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
-      if (row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 5) + (col0 >> 5)] = make_float2(mean, m2);
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
+        if (row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 5) + (col0 >> 5)] = make_float2(mean, m2);
+      }
       uint4 w2[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -348,51 +332,11 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
         w2[j] = make_uint4(pack_bf16x2(v[8 * j] * s0.x, v[8 * j + 1] * s0.y), pack_bf16x2(v[8 * j + 2] * s0.z, v[8 * j + 3] * s0.w),
                            pack_bf16x2(v[8 * j + 4] * s1.x, v[8 * j + 5] * s1.y), pack_bf16x2(v[8 * j + 6] * s1.z, v[8 * j + 7] * s1.w));
       }
-      epi_store_staged<OUT_BF16>(v, st, HALF, p, col0, w2);
+      epi_store_tma<OUT_BF16>(v, st, HALF, col0, w2);
       return;
     }
   }
-  if (st.buf != nullptr) {
-    if (p.out2 != nullptr && row_ok) {
-      __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (col0 + j < p.N)
-          *reinterpret_cast<uint4*>(o2 + j) =
-              make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                         pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-      }
-    }
-    epi_store_staged<OUT_BF16>(v, st, HALF, p, col0);   // all 128 threads take part (barrier inside)
-    return;
-  }
-  if (!row_ok) return;
-  if (p.out2 != nullptr) {
-    __nv_bfloat16* o2 = p.out2 + (size_t)row * p.ldo2 + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (col0 + j < p.N)
-        *reinterpret_cast<uint4*>(o2 + j) =
-            make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                       pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-    }
-  }
-  if (OUT_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (col0 + j < p.N)
-        *reinterpret_cast<uint4*>(o + j) =
-            make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                       pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      if (col0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-  }
+  epi_store_tma<OUT_BF16>(v, st, HALF, col0);   // all 128 threads of the group take part (barrier inside)
 }
 
 // Drains one accumulator tile of BN columns: TMEM base `tmem_acc` (lane group already applied).

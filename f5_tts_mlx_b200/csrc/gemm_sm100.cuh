@@ -58,7 +58,8 @@ struct GemmEpi {
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
 __global__ void __launch_bounds__(GemmEpi<BN, kStages>::kThreads, (kStages > 4) ? 1 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
-                    const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
+                    const __grid_constant__ CUtensorMap tma_out2, const GemmParams p) {
   using S = GemmSmem<BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
@@ -92,6 +93,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_out);
+    if (p.out2 != nullptr) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -230,8 +233,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.buf = smem + grp * 32768;
       stg.et = et;
       stg.r = r_in_tile;
-      stg.row0 = row0;
-      stg.rows_valid = p.tiles_per_batch > 0 ? min(128, p.rows_per_batch - m_in_batch0) : min(128, p.M - row0);
+      stg.map_out = &tma_out;
+      stg.map_out2 = &tma_out2;
+      stg.c1 = m_in_batch0;
+      stg.c2 = p.tiles_per_batch > 0 ? batch : 0;
       stg.bar_id = 1 + grp;
       stg.probe_cta = cta_lin;
       stg.buf2 = smem + 65536 + grp * 16384;
@@ -246,6 +251,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                  row_valid, stg, 0, 1, scale_s);
       }
     }
+    if (et == 0) tma_store_wait<0>();   // this group's TMA stores have landed before the CTA retires
     tc_fence_before();
     if (warp == 2 + 4 * (GemmEpi<BN, kStages>::kGroups - 1) && lane == 0) ts_mark(p, cta_lin, 8);
   }

@@ -107,6 +107,28 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   return 0;
 }
 
+int make_tmap_out(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t batches,
+                  uint64_t ld_elems) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(F5_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(F5_ERR_INVALID, "TMA store base pointer %p not 16-byte aligned", base);
+  if ((ld_elems * elem_bytes) % 16 != 0)
+    return set_error(F5_ERR_INVALID, "TMA store row pitch %llu bytes not a multiple of 16",
+                     (unsigned long long)(ld_elems * elem_bytes));
+  cuuint64_t gdim[3] = {cols, rows, batches};
+  cuuint64_t gstr[2] = {ld_elems * elem_bytes, ld_elems * elem_bytes * rows};
+  cuuint32_t bx[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(F5_ERR_CUDA, "cuTensorMapEncodeTiled (output map) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // launch accounting / profiling
 // ---------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ int launch_ln_f32(const float* x, float* y, int rows, int dim, const float* w, c
 int launch_dwconv7_ln(const float* x, void* y, int B, int N, int C, const float* wt,
                       const float* wb, const float* ln_w, const float* ln_b, cudaStream_t st);
 int launch_grn(const void* h, void* y, float* nx_scratch, const float* gamma, const float* beta,
-               int B, int N, int C, cudaStream_t st);
+               int B, int N, int C, cudaStream_t st, const int* valid_len = nullptr);
 int launch_text_embed_gather(const int* text, int B, int nt, int N, int C, const float* emb,
                              const float* pos_table, int max_pos, float* x, int Bout,
                              int drop_from, cudaStream_t st, int mask_padding = 1);
