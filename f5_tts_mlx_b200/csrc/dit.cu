@@ -42,6 +42,24 @@ static int check_common(const f5_dit_weights* w, const f5_dit_buffers* b) {
   return 0;
 }
 
+// Tuning aid: F5_TUNE="qkv=2:192,out=1:128,ff1=1:128,ff2=1:64" overrides (variant:tile_n) of the block's GEMMs so the
+// kernel-variant space can be measured in situ (bench.py) without rebuilding; unset = the launcher's own heuristics.
+struct GemmTune { int variant, tile_n; };
+static GemmTune tune_of(const char* key) {
+  GemmTune t = {0, 0};
+  const char* env = getenv("F5_TUNE");
+  if (!env) return t;
+  const char* p = strstr(env, key);
+  if (!p) return t;
+  p += strlen(key);
+  if (*p != '=') return t;
+  t.variant = atoi(p + 1);
+  const char* c = strchr(p, ':');
+  const char* comma = strchr(p, ',');
+  if (c && (!comma || c < comma)) t.tile_n = atoi(c + 1);
+  return t;
+}
+
 static long long ln_tab_ld(const f5_dit_weights* w) {
   return (long long)w->depth * (3 * w->dim + w->ff_inner) + 128;
 }
@@ -149,6 +167,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   if (pf_env < 0) { const char* v = getenv("F5_PREFETCH"); pf_env = (v && v[0] == '0') ? 0 : 1; }
   const bool prefetch = pf_env && R <= 16384;
   const bool fused = ln_fused(b);
+  static const GemmTune t_qkv = tune_of("qkv"), t_out = tune_of("out"), t_ff1 = tune_of("ff1"), t_ff2 = tune_of("ff2");
   const long long tab_ld = ln_tab_ld(w);
   const float* tab = fused ? b->ln_tab + (size_t)4 * ti * tab_ld : nullptr;   // this time's 4 operand rows
 
@@ -192,6 +211,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.qkv_w, D, R, 3 * D, D, b->qkv_bf16, 3 * D, true);
       g.bias = bw.qkv_b;
       if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F); g.ln_tab_ld = tab_ld; }
+      g.variant = t_qkv.variant; g.tile_n = t_qkv.tile_n;
       g.rows_per_batch = N; g.num_batches = BU;
       g.rope = b->rope; g.rope_cols = 2 * D; g.q_scale = 0.125f; g.q_cols = D;
       // weight prefetch chain (L2): while QKV runs, pull in out_w and ff1_w (contiguous in the pack)
@@ -209,6 +229,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.resid = b->x; g.ldr = D;
       if (prefetch) { g.prefetch = bw.ff1_w; g.prefetch_bytes = (int64_t)2 * F * D; }
       if (fused) { g.ln_scale = m + 4 * D; g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D; }   // ff_norm
+      g.variant = t_out.variant; g.tile_n = t_out.tile_n;
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
     if (!fused)
@@ -217,6 +238,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.ff1_w, D, R, F, D, b->ff_bf16, F, true);
       g.bias = bw.ff1_b; g.act = F5_ACT_GELU_TANH;
       if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F) + 3 * D; g.ln_tab_ld = tab_ld; }
+      g.variant = t_ff1.variant; g.tile_n = t_ff1.tile_n;
       if (prefetch) { g.prefetch = bw.ff2_w; g.prefetch_bytes = (int64_t)2 * D * F; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
@@ -233,6 +255,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
         g.ln_scale = (l + 1 < w->depth) ? mod + (size_t)(l + 1) * 6 * D + D : mod + (size_t)w->depth * 6 * D;
         g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D;
       }
+      g.variant = t_ff2.variant; g.tile_n = t_ff2.tile_n;
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
   }

@@ -127,11 +127,11 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   }
   if (a->ln_scale) {   // fused-LN producer mode
     F5_REQUIRE(!a->out_bf16 && a->out2_bf16 && a->ln_stats, "f5_gemm_bf16: ln_scale needs an fp32 out, out2_bf16 and ln_stats");
-    F5_REQUIRE(a->n % 32 == 0 && !a->rope, "f5_gemm_bf16: ln_scale needs n %% 32 == 0");
+    F5_REQUIRE(a->n % 64 == 0 && !a->rope, "f5_gemm_bf16: ln_scale needs n %% 64 == 0");
   }
   if (a->ln_in_stats) {   // fused-LN consumer mode
-    F5_REQUIRE(a->ln_tab && a->ln_tab_ld >= a->n && !a->gate && taps == 1 && a->k % 64 == 0,
-               "f5_gemm_bf16: ln_in_stats needs ln_tab (ld >= n), no gate, a plain GEMM with k %% 64 == 0");
+    F5_REQUIRE(a->ln_tab && a->ln_tab_ld >= a->n && !a->out2_bf16 && taps == 1 && a->k % 128 == 0,
+               "f5_gemm_bf16: ln_in_stats needs ln_tab (ld >= n), no second output, a plain GEMM with k %% 128 == 0");
   }
   if (a->resid) F5_REQUIRE(a->ldr % 4 == 0, "f5_gemm_bf16: ldr not multiple of 4");
   if (a->gate) F5_REQUIRE(a->gate_ld % 4 == 0, "f5_gemm_bf16: gate_ld not multiple of 4");
@@ -201,7 +201,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     p2.w_static = a->w_static;
     p2.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p2.pf_bytes = a->prefetch_bytes;
     p2.ln_scale = a->ln_scale; p2.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
-    p2.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p2.ln_in_units = a->k / 32;
+    p2.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p2.ln_in_units = a->k / 64;
     p2.ln_tab = a->ln_tab; p2.ln_tab_ld = a->ln_tab_ld;
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
@@ -263,7 +263,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   p.w_static = a->w_static;
   p.pf_ptr = reinterpret_cast<const char*>(a->prefetch); p.pf_bytes = a->prefetch_bytes;
   p.ln_scale = a->ln_scale; p.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
-  p.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p.ln_in_units = a->k / 32;
+  p.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p.ln_in_units = a->k / 64;
   p.ln_tab = a->ln_tab; p.ln_tab_ld = a->ln_tab_ld;
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 

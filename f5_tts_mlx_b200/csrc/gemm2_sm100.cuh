@@ -88,8 +88,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
                : "memory");
 }
 
-// LNO: the instantiation supports the fused-LN producer mode (fp32 output, 256-wide tiles): a third column vector
-// (1 + scale) per accumulator stage and one 8 KB bf16 staging buffer per epilogue group
+// LNO: the instantiation supports a second (bf16) output — the fused-LN producer mode — (fp32 output, 256-wide tiles):
+// one more 8 KB staging buffer per epilogue group
 template <int BN, int kStages, bool LNO = false>
 struct Gemm2Smem {
   static constexpr int kABytes = 128 * 64 * 2;
@@ -97,8 +97,8 @@ struct Gemm2Smem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
-  static constexpr int kColVecs = LNO ? 3 : 2;
-  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN][, scale_s[BN]])
+  static constexpr int kColVecs = 3;
+  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN], aux_s[BN])
   static constexpr int kStageOutOffset = (kColsOffset + 2 * kColVecs * BN * 4 + 1023) & ~1023;   // 2 x 16 KB store staging per group
   static constexpr int kStage2Offset = kStageOutOffset + 2 * 32768;                  // 8 KB per group (LNO)
   static constexpr int kTotal = kStage2Offset + (LNO ? 2 * 8192 : 0) + 1024;  // + align slack
@@ -285,14 +285,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       // operand staging for this tile (overlaps the MMAs still filling the accumulator)
       float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * S::kColVecs * BN;
       float* gate_s = bias_s + BN;
-      float* scale_s = LNO ? gate_s + BN : nullptr;
-      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, scale_s);   // both groups write the same values
+      float* aux_s = gate_s + BN;
+      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, aux_s);   // both groups write the same values
       float ln_mu_r, ln_rstd;
       epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
+      constexpr bool kHalves = ((BN / 64) % 2 == 1);   // odd unit count: the groups split every unit instead (gemm_epilogue.cuh)
       float2 cs[ROPE ? 32 : 1];
-      epi_load_rope<ROPE>(p, pos, cs);
       float4 res0[8];
-      epi_load_resid(p, row, n0 + grp * 64, row_ok, res0);
+      if constexpr (kHalves) {
+        epi_load_rope_half<ROPE>(p, pos, cs, grp);
+      } else {
+        epi_load_rope<ROPE>(p, pos, cs);
+        epi_load_resid(p, row, n0 + grp * 64, row_ok, res0);
+      }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 
       mbar_wait(&tmem_full_bar[as], aph);
@@ -317,9 +322,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         stg.c1 = m_tile * 256 + (int)rank * 128;
         stg.c2 = 0;
       }
-      epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tmem_base + as * BN + ((uint32_t)(lg * 32) << 16), bias_s,
-                                              gate_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid, stg, grp, 2,
-                                              scale_s);
+      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(lg * 32) << 16);
+      if constexpr (kHalves) {
+        if (grp == 0)
+          epi_drain_tile_half<BN, ACT, OUT_BF16, ROPE, 0>(tacc, bias_s, gate_s, aux_s, cs, p, n0, row, b_idx, row_ok, row_valid, stg);
+        else
+          epi_drain_tile_half<BN, ACT, OUT_BF16, ROPE, 1>(tacc, bias_s, gate_s, aux_s, cs, p, n0, row, b_idx, row_ok, row_valid, stg);
+      } else {
+        epi_drain_tile<BN, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, aux_s, cs, res0, p, n0, row, b_idx, row_ok, row_valid,
+                                                stg, grp, 2);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);

@@ -7,6 +7,10 @@ namespace f5 {
 
 enum GemmAct { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_MISH = 3 };
 
+#ifndef F5_EPI_WAIT_MODE
+#define F5_EPI_WAIT_MODE 0
+#endif
+
 struct GemmParams {
   int M, N, K;             // logical problem (flat mode: M rows; batched mode: see below)
   // row mapping
@@ -41,12 +45,12 @@ struct GemmParams {
   // ---- fused AdaLayerNormZero (dit.py:270,289,321), by linearity of the consuming Linear ----
   //   Linear(LN(x) (1+s) + b) = rstd * ( (x (1+s)) W^T - mean * c1 ) + c2,  c1 = (1+s) W^T,  c2 = b W^T + bias
   // producer side (this GEMM writes the fp32 residual stream x): out2 <- bf16(x * (1 + ln_scale[col])) through the
-  // staged store path, ln_stats[row][col/32] <- (mean, M2) of each 32-column chunk of the row
+  // staged store path, ln_stats[row][col/64] <- (sum, sum of squares) of each 64-column unit of the row
   const float* ln_scale;   // [N] scale vector of the NEXT AdaLN, or null
-  float2* ln_stats;        // [rows][N/32]
+  float2* ln_stats;        // [rows][N/64]
   // consumer side (A is such an out2 matrix): the epilogue finishes the LayerNorm
-  const float2* ln_in_stats;  // [rows][K/32] or null
-  int ln_in_units;            // K/32
+  const float2* ln_in_stats;  // [rows][K/64] or null
+  int ln_in_units;            // K/64
   const float* ln_tab;        // 4 rows of ln_tab_ld floats: c1_hi, c1_lo, c2_hi, c2_lo (bf16-split operand rows of
   long long ln_tab_ld;        //   the table GEMM), already offset to this GEMM's column 0
 };
@@ -101,46 +105,44 @@ __device__ __forceinline__ float mish_fast(float x) {
 
 // stage bias[n0..n0+BN) and gate[n0..n0+BN) (gate only when it is shared by all utterances,
 // gate_ld == 0) into shared memory; called by the 128 epilogue threads, `et` = 0..127
-// With the fused-LN consumer mode gate_s holds c1 and bias_s holds c2 + bias (such GEMMs have no gate); with the
-// producer mode scale_s (may be null when the instantiation has no fp32 output) holds 1 + ln_scale.
+// aux_s: c1 of the fused-LN consumer mode, or the second output's scale 1 + ln_scale (1 when there is none) — a GEMM is
+// never both.  In consumer mode bias_s holds c2 + bias.
 template <int BN>
 __device__ __forceinline__ void epi_stage_cols(const GemmParams& p, int n0, int et, float* bias_s,
-                                               float* gate_s, float* scale_s = nullptr) {
+                                               float* gate_s, float* aux_s) {
 #pragma unroll
   for (int i = et; i < BN; i += 128) {
     const int col = n0 + i;
     const bool ok = col < p.N;
     float b = (p.bias != nullptr && ok) ? p.bias[col] : 0.f;
-    float g = (p.gate != nullptr && p.gate_ld == 0 && ok) ? p.gate[col] : 1.f;
+    float x = (p.ln_scale != nullptr && ok) ? 1.f + p.ln_scale[col] : 1.f;
     if (p.ln_in_stats != nullptr && ok) {
       const float* t = p.ln_tab + col;
-      g = t[0] + t[p.ln_tab_ld];
+      x = t[0] + t[p.ln_tab_ld];
       b += t[2 * p.ln_tab_ld] + t[3 * p.ln_tab_ld];
     }
     bias_s[i] = b;
-    gate_s[i] = g;
-    if (scale_s != nullptr) scale_s[i] = (p.ln_scale != nullptr && ok) ? 1.f + p.ln_scale[col] : 1.f;
+    gate_s[i] = (p.gate != nullptr && p.gate_ld == 0 && ok) ? p.gate[col] : 1.f;
+    aux_s[i] = x;
   }
 }
 
-// consumer side of the fused LN: combine the row's per-chunk (mean, M2) pairs (equal counts of 32, fixed order =>
-// deterministic) into (mean * rstd, rstd); eps as nn.LayerNorm(eps=1e-6) (dit.py:262,281)
+// consumer side of the fused LN: the row's (sum, sum of squares) per 64-column unit, added in a fixed order
+// (deterministic), -> (mean * rstd, rstd); eps as nn.LayerNorm(eps=1e-6) (dit.py:262,281).  Without the mode the
+// pair is (0, 1), which makes the epilogue's rstd * acc - mu_r * c1 + bias the plain acc + bias.
 __device__ __forceinline__ void epi_load_ln_row(const GemmParams& p, int row, bool row_ok, float& mu_r, float& rstd) {
   mu_r = 0.f; rstd = 1.f;
   if (p.ln_in_stats == nullptr || !row_ok) return;
   const float4* st = reinterpret_cast<const float4*>(p.ln_in_stats + (size_t)row * p.ln_in_units);
-  float mean = 0.f, m2 = 0.f;
+  float s1 = 0.f, s2 = 0.f;
   for (int u = 0; u < p.ln_in_units; u += 2) {
-    const float4 v = st[u >> 1];                       // (mean, M2) of chunks u and u + 1
-    const float inv0 = __fdividef(1.f, (float)(u + 1)), inv1 = __fdividef(1.f, (float)(u + 2));
-    float d = v.x - mean;
-    mean = fmaf(d, inv0, mean);
-    m2 += v.y + d * d * (32.f * u) * inv0;
-    d = v.z - mean;
-    mean = fmaf(d, inv1, mean);
-    m2 += v.w + d * d * (32.f * (u + 1)) * inv1;
+    const float4 v = st[u >> 1];
+    s1 += v.x; s2 += v.y;
+    s1 += v.z; s2 += v.w;
   }
-  rstd = rsqrtf(m2 / (32.f * p.ln_in_units) + 1e-6f);
+  const float inv_k = 1.f / (64.f * p.ln_in_units);
+  const float mean = s1 * inv_k;
+  rstd = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + 1e-6f);
   mu_r = mean * rstd;
 }
 
@@ -153,6 +155,21 @@ __device__ __forceinline__ void epi_load_rope(const GemmParams& p, int pos, floa
       const float4 v = rp[j];
       cs[2 * j] = make_float2(v.x, v.y);
       cs[2 * j + 1] = make_float2(v.z, v.w);
+    }
+  }
+}
+
+// only the (cos, sin) pairs of one 32-column half of a head: cs[16 half .. 16 half + 16)
+template <bool ROPE>
+__device__ __forceinline__ void epi_load_rope_half(const GemmParams& p, int pos, float2 (&cs)[ROPE ? 32 : 1], int half) {
+  if (ROPE) {
+    const float4* rp = reinterpret_cast<const float4*>(p.rope + (size_t)pos * 32 + half * 16);
+    if (half == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 v = rp[j]; cs[2 * j] = make_float2(v.x, v.y); cs[2 * j + 1] = make_float2(v.z, v.w); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 v = rp[j]; cs[16 + 2 * j] = make_float2(v.x, v.y); cs[17 + 2 * j] = make_float2(v.z, v.w); }
     }
   }
 }
@@ -187,7 +204,8 @@ struct EpiStage {
   const CUtensorMap* map_out;   // (cols, rows per utterance, utterances) of `out` / `out2`
   const CUtensorMap* map_out2;
   int c1, c2;              // tensor-map coordinates of tile row 0: row inside the utterance, utterance
-  float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics
+  int par_base;            // staging buffer of a chunk = par_base ^ HALF (set by the drain loops)
+  float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics ((0, 1) otherwise)
 };
 
 // `w2`: the chunk's second output (bf16, 4 x uint4 per row) or nullptr
@@ -196,11 +214,18 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
                                               const uint4* w2 = nullptr) {
   uint8_t* buf = st.buf + par * 16384;
   uint8_t* buf2 = st.buf2 + par * st.buf2_par;
+#if F5_EPI_WAIT_MODE == 1
+  // two barriers per chunk: the buffer about to be rewritten was the source of the store before the previous one;
+  // the previous chunk's store may still be in flight while this chunk is computed and staged
+  if (st.et == 0) { if (w2 != nullptr && st.buf2_par == 0) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+  asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
+#else
   if (w2 != nullptr && st.buf2_par == 0) {
     // one staging buffer for the second output: the previous chunk's store must have read it
     if (st.et == 0) tma_store_wait_read<0>();
     asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
   }
+#endif
   if (OUT_BF16) {
     uint8_t* mine = buf + st.r * 64;
     const int sw = (st.r >> 1) & 3;
@@ -223,9 +248,11 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
     for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
   }
   fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA unit
+#if F5_EPI_WAIT_MODE != 1
   // the OTHER staging buffer is rewritten by the next chunk: every store issued so far must have read its source
   // (the previous chunk's store was issued a whole chunk of work ago)
   if (st.et == 0) tma_store_wait_read<0>();
+#endif
   asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
   if (st.et == 0) {
     tma_store_3d(st.map_out, buf, col0, st.c1, st.c2);
@@ -235,33 +262,24 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
 }
 
 // HALF: which 32-column half of a 64-column head this chunk is (static RoPE register indexing)
+// `unit_acc`: running (sum, sum of squares) of this thread's row over the 64-column unit (HALF 0 starts it, HALF 1
+// completes and stores it) — fused-LN producer mode only.
 template <int ACT, bool OUT_BF16, bool ROPE, int HALF>
 __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float4 (&res)[8],
-                                          const float* bias_s, const float* gate_s,
+                                          const float* bias_s, const float* gate_s, const float* aux_s,
                                           const float2 (&cs)[ROPE ? 32 : 1], const GemmParams& p,
                                           int col0, int row, int b_idx, bool row_ok, bool row_valid,
-                                          const EpiStage& st, const float* scale_s = nullptr) {
+                                          const EpiStage& st, float2& unit_acc) {
   float v[32];
-  if (p.ln_in_stats != nullptr) {
-    // fused-LN consumer: rstd * acc - (mean * rstd) * c1 + (c2 + bias)   (gate_s = c1, bias_s = c2 + bias)
+  // rstd * acc - (mean * rstd) * c1 + (c2 + bias): the fused-LN consumer; (mu_r, rstd) = (0, 1) otherwise
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
-      const float4 cc = *reinterpret_cast<const float4*>(gate_s + j);
-      v[j] = fmaf(__uint_as_float(acc[j]), st.rstd, fmaf(-st.mu_r, cc.x, bb.x));
-      v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), st.rstd, fmaf(-st.mu_r, cc.y, bb.y));
-      v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), st.rstd, fmaf(-st.mu_r, cc.z, bb.z));
-      v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), st.rstd, fmaf(-st.mu_r, cc.w, bb.w));
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
-      v[j] = __uint_as_float(acc[j]) + bb.x;
-      v[j + 1] = __uint_as_float(acc[j + 1]) + bb.y;
-      v[j + 2] = __uint_as_float(acc[j + 2]) + bb.z;
-      v[j + 3] = __uint_as_float(acc[j + 3]) + bb.w;
-    }
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+    const float4 cc = *reinterpret_cast<const float4*>(aux_s + j);
+    v[j] = fmaf(__uint_as_float(acc[j]), st.rstd, fmaf(-st.mu_r, cc.x, bb.x));
+    v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), st.rstd, fmaf(-st.mu_r, cc.y, bb.y));
+    v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), st.rstd, fmaf(-st.mu_r, cc.z, bb.z));
+    v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), st.rstd, fmaf(-st.mu_r, cc.w, bb.w));
   }
   if (ACT == ACT_GELU_TANH) {
 #pragma unroll
@@ -292,7 +310,7 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
-  if (p.gate != nullptr && p.ln_in_stats == nullptr) {
+  if (p.gate != nullptr) {
     if (p.gate_ld == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -311,32 +329,29 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
     v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
   }
   if constexpr (!OUT_BF16) {
-    if (p.out2 != nullptr && scale_s != nullptr) {
-      // second output: bf16(v * scale) — the fused-LN operand x * (1 + s) of the GEMM that consumes LN(x) (scale_s = 1
-      // when no ln_scale is given: a plain bf16 copy); with ln_stats also the chunk statistics of the finished row
+    if (p.out2 != nullptr) {
+      // second output: bf16(v * aux) — the fused-LN operand x * (1 + s) of the GEMM that consumes LN(x) (aux = 1 when
+      // no ln_scale is given: a plain bf16 copy); with ln_stats also the unit statistics of the finished row
       if (p.ln_stats != nullptr) {
-        float sum = 0.f;
+        float s1 = HALF == 0 ? 0.f : unit_acc.x, s2 = HALF == 0 ? 0.f : unit_acc.y;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += v[j];
-        const float mean = sum * (1.f / 32.f);
-        float m2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; m2 = fmaf(d, d, m2); }
-        if (row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 5) + (col0 >> 5)] = make_float2(mean, m2);
+        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+        unit_acc = make_float2(s1, s2);
+        if (HALF == 1 && row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 6) + (col0 >> 6)] = unit_acc;
       }
       uint4 w2[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 s0 = *reinterpret_cast<const float4*>(scale_s + 8 * j);
-        const float4 s1 = *reinterpret_cast<const float4*>(scale_s + 8 * j + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(aux_s + 8 * j);
+        const float4 s1 = *reinterpret_cast<const float4*>(aux_s + 8 * j + 4);
         w2[j] = make_uint4(pack_bf16x2(v[8 * j] * s0.x, v[8 * j + 1] * s0.y), pack_bf16x2(v[8 * j + 2] * s0.z, v[8 * j + 3] * s0.w),
                            pack_bf16x2(v[8 * j + 4] * s1.x, v[8 * j + 5] * s1.y), pack_bf16x2(v[8 * j + 6] * s1.z, v[8 * j + 7] * s1.w));
       }
-      epi_store_tma<OUT_BF16>(v, st, HALF, col0, w2);
+      epi_store_tma<OUT_BF16>(v, st, st.par_base ^ HALF, col0, w2);
       return;
     }
   }
-  epi_store_tma<OUT_BF16>(v, st, HALF, col0);   // all 128 threads of the group take part (barrier inside)
+  epi_store_tma<OUT_BF16>(v, st, st.par_base ^ HALF, col0);   // all 128 threads of the group take part (barrier inside)
 }
 
 // Drains one accumulator tile of BN columns: TMEM base `tmem_acc` (lane group already applied).
@@ -344,12 +359,13 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 // interleave units in the CTA-pair kernel); `res0` holds the residual of unit cc0's first 32 columns.
 template <int BN, int ACT, bool OUT_BF16, bool ROPE>
 __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* bias_s,
-                                               const float* gate_s, const float2 (&cs)[ROPE ? 32 : 1],
+                                               const float* gate_s, const float* aux_s, const float2 (&cs)[ROPE ? 32 : 1],
                                                float4 (&res0)[8], const GemmParams& p, int n0, int row,
                                                int b_idx, bool row_ok, bool row_valid,
-                                               const EpiStage& st, int cc0 = 0, int cc_step = 1,
-                                               const float* scale_s = nullptr) {
+                                               EpiStage& st, int cc0 = 0, int cc_step = 1) {
   float4 res1[8];
+  float2 unit_acc = make_float2(0.f, 0.f);
+  st.par_base = 0;
 #pragma unroll 1
   for (int cc = cc0; cc < BN / 64; cc += cc_step) {
     const int colA = n0 + cc * 64, colB = colA + 32;
@@ -359,15 +375,41 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
     tmem_ld32(tmem_acc + cc * 64, acc);
     tmem_wait_ld();
     if (colA < p.N)   // uniform per CTA
-      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
-                                        b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 : nullptr);
+      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res0, bias_s + cc * 64, gate_s + cc * 64, aux_s + cc * 64, cs, p, colA, row,
+                                        b_idx, row_ok, row_valid, st, unit_acc);
     // chunk B: request the next unit's first residual, then drain B
     if (cc + cc_step < BN / 64) epi_load_resid(p, row, colA + 64 * cc_step, row_ok, res0);
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)
-      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res1, bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs, p,
-                                        colB, row, b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 + 32 : nullptr);
+      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res1, bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, aux_s + cc * 64 + 32, cs, p,
+                                        colB, row, b_idx, row_ok, row_valid, st, unit_acc);
+  }
+}
+
+// Tiles whose unit count is odd (192 columns = 3 heads: QKV at batch 1) would leave one group of 4 warps with twice
+// the work of the other; here group g takes the HALF-g chunk (32 columns) of EVERY unit instead — equal work, and each
+// thread needs only its half of the RoPE table (cs[16 g .. 16 g + 16)).  No second output / unit statistics in this
+// mode (bf16 outputs only); staging buffers alternate per unit.
+template <int BN, int ACT, bool OUT_BF16, bool ROPE, int HALF>
+__device__ __forceinline__ void epi_drain_tile_half(uint32_t tmem_acc, const float* bias_s, const float* gate_s,
+                                                    const float* aux_s, const float2 (&cs)[ROPE ? 32 : 1],
+                                                    const GemmParams& p, int n0, int row, int b_idx, bool row_ok,
+                                                    bool row_valid, EpiStage& st) {
+  float4 res[2][8];
+  float2 unit_acc = make_float2(0.f, 0.f);
+  epi_load_resid(p, row, n0 + HALF * 32, row_ok, res[0]);
+#pragma unroll
+  for (int cc = 0; cc < BN / 64; ++cc) {
+    const int col = n0 + cc * 64 + HALF * 32;
+    uint32_t acc[32];
+    if (cc + 1 < BN / 64) epi_load_resid(p, row, col + 64, row_ok, res[(cc + 1) & 1]);
+    tmem_ld32(tmem_acc + cc * 64 + HALF * 32, acc);
+    tmem_wait_ld();
+    st.par_base = (cc & 1) ^ HALF;      // staging buffer cc & 1
+    if (col < p.N)
+      epi_apply<ACT, OUT_BF16, ROPE, HALF>(acc, res[cc & 1], bias_s + cc * 64 + HALF * 32, gate_s + cc * 64 + HALF * 32,
+                                           aux_s + cc * 64 + HALF * 32, cs, p, col, row, b_idx, row_ok, row_valid, st, unit_acc);
   }
 }
 
@@ -377,12 +419,13 @@ __device__ __forceinline__ void epi_drain_tile(uint32_t tmem_acc, const float* b
 // chunk: its per-chunk work is much shorter than the latency it tries to cover).
 template <int BN, int ACT, bool OUT_BF16, bool ROPE>
 __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, const float* bias_s,
-                                                         const float* gate_s,
+                                                         const float* gate_s, const float* aux_s,
                                                          const float2 (&cs)[ROPE ? 32 : 1],
                                                          float4 (&res)[BN / 32][8], const GemmParams& p,
                                                          int n0, int row, int b_idx, bool row_ok,
-                                                         bool row_valid, const EpiStage& st,
-                                                         const float* scale_s = nullptr) {
+                                                         bool row_valid, EpiStage& st) {
+  float2 unit_acc = make_float2(0.f, 0.f);
+  st.par_base = 0;
 #pragma unroll
   for (int cc = 0; cc < BN / 64; ++cc) {
     const int colA = n0 + cc * 64, colB = colA + 32;
@@ -393,16 +436,16 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
     if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 3);
 #endif
     if (colA < p.N)
-      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, cs, p, colA, row,
-                                        b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 : nullptr);
+      epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, aux_s + cc * 64, cs, p, colA, row,
+                                        b_idx, row_ok, row_valid, st, unit_acc);
 #ifdef F5_EPI_PROBE
     if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 4);
 #endif
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)
-      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res[2 * cc + 1], bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, cs,
-                                        p, colB, row, b_idx, row_ok, row_valid, st, scale_s ? scale_s + cc * 64 + 32 : nullptr);
+      epi_apply<ACT, OUT_BF16, ROPE, 1>(acc, res[2 * cc + 1], bias_s + cc * 64 + 32, gate_s + cc * 64 + 32, aux_s + cc * 64 + 32, cs,
+                                        p, colB, row, b_idx, row_ok, row_valid, st, unit_acc);
   }
 }
 

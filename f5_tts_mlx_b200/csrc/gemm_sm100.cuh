@@ -36,7 +36,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kColsOffset = (kBarOffset + (2 * kStages + 1) * 8 + 16 + 15) & ~15;   // bias_s[BN], gate_s[BN], scale_s[BN] (float4 reads)
+  static constexpr int kColsOffset = (kBarOffset + (2 * kStages + 1) * 8 + 16 + 15) & ~15;   // bias_s[BN], gate_s[BN], aux_s[BN] (float4 reads)
   static constexpr int kTotal = kColsOffset + 3 * BN * 4 + 1024;  // + align slack
   // epilogue store staging reuses the (idle) operand ring: fp32/bf16 chunks at [0, 64 KB) (32 KB per group), the
   // bf16 copy of the fused-LN producer mode at [64 KB, 96 KB) (16 KB per group, two alternating 8 KB buffers)
@@ -204,8 +204,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     // operand staging, overlapped with the main loop
     float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + grp * BNG;
     float* gate_s = reinterpret_cast<float*>(smem + S::kColsOffset) + BN + grp * BNG;
-    float* scale_s = OUT_BF16 ? nullptr : reinterpret_cast<float*>(smem + S::kColsOffset) + 2 * BN + grp * BNG;
-    epi_stage_cols<BNG>(p, n0g, et, bias_s, gate_s, scale_s);
+    float* aux_s = reinterpret_cast<float*>(smem + S::kColsOffset) + 2 * BN + grp * BNG;
+    epi_stage_cols<BNG>(p, n0g, et, bias_s, gate_s, aux_s);
     float ln_mu_r, ln_rstd;
     epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
     float2 cs[ROPE ? 32 : 1];
@@ -244,11 +244,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
       const uint32_t tacc = tmem_base + grp * BNG + ((uint32_t)(lg * 32) << 16);
       if constexpr (kPreloadAll) {
-        epi_drain_tile_preloaded<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all, p, n0g, row, b_idx,
-                                                           row_ok, row_valid, stg, scale_s);
+        epi_drain_tile_preloaded<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, aux_s, cs, res_all, p, n0g, row, b_idx,
+                                                           row_ok, row_valid, stg);
       } else {
-        epi_drain_tile<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, cs, res_all[0], p, n0g, row, b_idx, row_ok,
-                                                 row_valid, stg, 0, 1, scale_s);
+        epi_drain_tile<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, aux_s, cs, res_all[0], p, n0g, row, b_idx, row_ok,
+                                                 row_valid, stg, 0, 1);
       }
     }
     if (et == 0) tma_store_wait<0>();   // this group's TMA stores have landed before the CTA retires

@@ -84,7 +84,7 @@ class DitSession:
         # fused AdaLN (f5_gemm_args.ln_*): per-row chunk statistics, the c1/c2 operand tables of every consuming
         # Linear for every evaluation time, and the bf16 operand rows of the table GEMMs
         self.ln_tab_ld = cfg.depth * (3 * D + F) + 128
-        self.ln_stats = z(R, D // 32, 2) if fused_adaln else None
+        self.ln_stats = z(R, D // 64, 2) if fused_adaln else None
         self.ln_tab = z(4 * n_times, self.ln_tab_ld) if fused_adaln else None
         self.ln_prep = z(2 * cfg.depth + 1, 4 * n_times, D, dt=bf16) if fused_adaln else None
         c = DitBuffersC()

@@ -57,8 +57,8 @@ def gemm(
     debug_ts: torch.Tensor | None = None,
     out2: torch.Tensor | None = None,          # bf16 [rows, >=n] second copy (or the fused-LN operand, see ln_scale)
     ln_scale: torch.Tensor | None = None,      # f32 [n]: producer mode — out2 = bf16(out * (1 + ln_scale)), ln_stats filled
-    ln_stats: torch.Tensor | None = None,      # f32 [rows, n/32, 2]
-    ln_in_stats: torch.Tensor | None = None,   # f32 [rows, k/32, 2]: consumer mode
+    ln_stats: torch.Tensor | None = None,      # f32 [rows, n/64, 2] (sum, sum of squares) per 64 columns
+    ln_in_stats: torch.Tensor | None = None,   # f32 [rows, k/64, 2]: consumer mode
     ln_tab: torch.Tensor | None = None,        # f32 [4, >=n] rows c1_hi, c1_lo, c2_hi, c2_lo
 ) -> torch.Tensor:
     _need_cuda(a, w, out, bias, resid, gate, row_len, rope, out2, ln_scale, ln_stats, ln_in_stats, ln_tab)

@@ -112,12 +112,12 @@ typedef struct f5_gemm_args {
    * consumes the normalised activations:
    *     Linear(LN(x) * (1 + s) + b) = rstd * ((x * (1 + s)) W^T - mean * c1) + c2,   c1 = (1 + s) W^T,  c2 = b W^T.
    * Producer side (the GEMM whose fp32 `out` is the residual stream x): with `ln_scale` = s of the NEXT AdaLN,
-   * out2_bf16 receives bf16(out * (1 + s[col])) and ln_stats[row][col / 32] the (mean, M2) of each 32-column chunk
-   * of the finished row (requires out_bf16 == 0, n % 32 == 0).
-   * Consumer side (`a` is such an out2 matrix): with `ln_in_stats` = that statistics array ([rows][k / 32][2]) the
+   * out2_bf16 receives bf16(out * (1 + s[col])) and ln_stats[row][col / 64] the (sum, sum of squares) of each
+   * 64-column unit of the finished row (requires out_bf16 == 0, n % 64 == 0).
+   * Consumer side (`a` is such an out2 matrix): with `ln_in_stats` = that statistics array ([rows][k / 64][2]) the
    * epilogue computes rstd * (acc - mean * c1[col]) + c2[col] + bias[col] before the activation; ln_tab holds 4 rows
    * of ln_tab_ld floats — c1_hi, c1_lo, c2_hi, c2_lo (the table GEMM runs on a bf16 hi/lo split of (1 + s) and b,
-   * f5_dit_precompute) — already offset to this GEMM's column 0.  gate must be NULL. */
+   * f5_dit_precompute) — already offset to this GEMM's column 0.  A GEMM is producer or consumer, not both. */
   const float* ln_scale;
   float* ln_stats;
   const float* ln_in_stats;
@@ -251,7 +251,7 @@ typedef struct f5_dit_buffers {
   float* v;                   /* fp32 [rows, mel_dim]: DiT output (flow prediction) */
   /* Fused AdaLN (see f5_gemm_args.ln_*): all three non-NULL selects it, any NULL keeps the separate
    * f5_ln_modulate launches.  ln_tab_ld = depth*(3D + ff_inner) + 128 (f5_dit_ln_tab_ld). */
-  float* ln_stats;            /* fp32 [rows, D/32, 2]: per-row chunk statistics of the residual stream */
+  float* ln_stats;            /* fp32 [rows, D/64, 2]: per-row (sum, sum of squares) per 64 columns of the residual stream */
   float* ln_tab;              /* fp32 [4*n_times, ln_tab_ld]: c1/c2 operand rows per time, columns = per block [qkv 3D | ff1 F], then proj_out */
   void* ln_prep;              /* bf16 [2*depth+1, 4*n_times, D]: operand rows of the table GEMMs */
   /* Frame bucketing (plan reuse across utterances of different length): the buffers are sized for `frames` rows per

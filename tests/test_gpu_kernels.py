@@ -178,20 +178,19 @@ def _ln_tab(scale, shift, w):
                                                 (700, 1024, 1024, 2, 256), (40000, 1024, 2048, 0, 0)])
 def test_gemm_fused_ln_producer(M, D, K, variant, tile):
     """out-proj / FF2 shape: x = resid + gate * (a W^T + bias) in fp32, plus the bf16 operand x * (1 + s) and the
-    per-row chunk statistics (mean, M2 per 32 columns) of x — all three against fp32 torch."""
+    per-row unit statistics (sum, sum of squares per 64 columns) of x — all three against fp32 torch."""
     from f5_tts_mlx_b200 import ops
     a = rnd(M, K).bfloat16(); w = rnd(D, K, scale=K ** -0.5).bfloat16(); bias = rnd(D)
     gate = rnd(1, D); x = rnd(M, D) * 2 + 0.3; x0 = x.clone(); s = rnd(D, seed=5) * 0.3
     xt = torch.full((M, D), float("nan"), device=dev, dtype=torch.bfloat16)
-    stats = torch.full((M, D // 32, 2), float("nan"), device=dev)
+    stats = torch.full((M, D // 64, 2), float("nan"), device=dev)
     ops.gemm(a, w, x, bias=bias, resid=x, gate=gate[0], out2=xt, ln_scale=s, ln_stats=stats, variant=variant, tile_n=tile)
     ref = x0 + gate * (a.float() @ w.float().T + bias)
     assert rel(x, ref) < 1e-5
     assert rel(xt, ref * (1 + s)) < 4e-3
-    chunks = ref.view(M, D // 32, 32)
-    assert (stats[..., 0] - chunks.mean(-1)).abs().max().item() < 1e-4
-    m2 = ((chunks - chunks.mean(-1, keepdim=True)) ** 2).sum(-1)
-    assert rel(stats[..., 1], m2) < 1e-4
+    units = ref.view(M, D // 64, 64)
+    assert (stats[..., 0] - units.sum(-1)).abs().max().item() < 2e-3
+    assert rel(stats[..., 1], (units ** 2).sum(-1)) < 1e-5
 
 
 @pytest.mark.parametrize("M,D,N,act,rope", [(1874, 1024, 3072, 0, True), (1874, 1024, 2048, 1, False), (937, 1024, 100, 0, False),
@@ -205,8 +204,8 @@ def test_gemm_fused_ln_consumer(M, D, N, act, rope):
     s = rnd(D, seed=7) * 0.3; b = rnd(D, seed=8) * 0.5
     w = rnd(N, D, scale=D ** -0.5).bfloat16(); bias = rnd(N)
     xt = (x * (1 + s)).bfloat16()
-    chunks = x.view(M, D // 32, 32)
-    stats = torch.stack([chunks.mean(-1), ((chunks - chunks.mean(-1, keepdim=True)) ** 2).sum(-1)], dim=-1).contiguous()
+    units = x.view(M, D // 64, 64)
+    stats = torch.stack([units.sum(-1), (units ** 2).sum(-1)], dim=-1).contiguous()
     tab = _ln_tab(s, b, w)
     f32 = N == 100
     out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
