@@ -69,6 +69,19 @@ class GemmArgs(C.Structure):
     ]
 
 
+class DitDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim", "depth", "heads", "ff_inner", "mel_dim", "text_dim", "conv_layers",
+                                         "text_num_embeds")]
+
+
+class DitShape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "frames", "cfg", "n_times", "text_len_max", "masked", "fused_adaln",
+                                         "bucketed")]
+
+
+TENSOR_LOOKUP = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_int64))
+
+
 # exported symbols -> (restype, argtypes); tests check that every one of these resolves
 SYMBOLS: dict[str, tuple] = {
     "f5_last_error": (C.c_char_p, []),
@@ -103,6 +116,12 @@ SYMBOLS: dict[str, tuple] = {
     "f5_vocos_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "f5_ode_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f5_packed_weights_bytes": (C.c_int64, [C.POINTER(DitDims)]),
+    "f5_pack_weights": (C.c_int, [C.POINTER(DitDims), TENSOR_LOOKUP, C.c_void_p, C.c_void_p]),
+    "f5_bind_packed_weights": (C.c_int, [C.POINTER(DitDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f5_workspace_bytes": (C.c_int64, [C.POINTER(DitDims), C.POINTER(DitShape)]),
+    "f5_bind_workspace": (C.c_int, [C.POINTER(DitDims), C.POINTER(DitShape), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "f5_nccl_broadcast_weights": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -370,6 +370,42 @@ int f5_istft(const float* h, int64_t ldh, int32_t batch, int32_t frames, const f
 int f5_vocos_decode(const f5_vocos_weights* w, const f5_vocos_buffers* b, const float* mel,
                     float* wave, void* stream);
 
+/* ------------------------------------------------------------------------------------------ *
+ * Host utilities for hosts that are not Python (the package's weights.PackedDiT / dit.DitSession / parallel.py do
+ * the same from Python): sizing + packing + binding of the weight buffer, sizing + carving of the session workspace,
+ * and the ONE collective of the multi-GPU path.
+ *
+ * f5_pack_weights    : what F5TTS.from_pretrained + load_weights amount to for the DiT (cfm.py:455-517 after the key
+ *                      conversion): `get(user, mlx_name, &numel)` returns the fp32 HOST tensor of an MLX-named parameter
+ *                      ("transformer.transformer_blocks.3.attn.to_q.weight", MLX layouts) or NULL; host_out receives
+ *                      f5_packed_weights_bytes() bytes in the layout every kernel expects (copy it to the device,
+ *                      then f5_bind_packed_weights on the device copy).
+ * f5_bind_workspace  : carves f5_dit_buffers out of one 256-byte-aligned device block of f5_workspace_bytes(), zeroes
+ *                      it and uploads the RoPE table; the caller then fills text / text_len / seq_len / cond / tvals.
+ * f5_nccl_broadcast_weights : ncclBroadcast of the packed buffer from `root` ("a single NCCL broadcast of
+ *                      weights at load, no per-step collective"); `nccl_comm` is an initialised ncclComm_t; the NCCL
+ *                      symbol is taken from the library already loaded in the process (or libnccl.so.2).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct f5_dit_dims {
+  int32_t dim, depth, heads, ff_inner, mel_dim, text_dim, conv_layers, text_num_embeds;
+} f5_dit_dims;
+typedef struct f5_dit_shape {
+  int32_t batch, frames, cfg, n_times, text_len_max;
+  int32_t masked;        /* allocate seq_len (batch > 1, cfm.py:333-336)            */
+  int32_t fused_adaln;   /* allocate ln_stats / ln_tab / ln_prep                    */
+  int32_t bucketed;      /* allocate valid_len (frames is a bucket size)            */
+} f5_dit_shape;
+typedef const float* (*f5_tensor_lookup)(void* user, const char* mlx_name, int64_t* numel);
+
+int64_t f5_packed_weights_bytes(const f5_dit_dims* d);
+int f5_pack_weights(const f5_dit_dims* d, f5_tensor_lookup get, void* user, void* host_out);
+int f5_bind_packed_weights(const f5_dit_dims* d, const void* device_base, f5_dit_weights* out,
+                           f5_convnext_weights* text_blocks /* [conv_layers] */,
+                           f5_dit_block_weights* blocks /* [depth] */);
+int64_t f5_workspace_bytes(const f5_dit_dims* d, const f5_dit_shape* s);
+int f5_bind_workspace(const f5_dit_dims* d, const f5_dit_shape* s, void* device_base, f5_dit_buffers* out, void* stream);
+int f5_nccl_broadcast_weights(void* device_buf, int64_t bytes, int32_t root, void* nccl_comm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,42 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 
+def c_abi_broadcast_check(model, rank, world, dev):
+    """f5_nccl_broadcast_weights (the C entry a non-Python host uses for the ONE collective of the path) on a raw
+    ncclComm_t created through NCCL's C API: every non-root rank scrambles a copy of the packed buffer, the call must
+    restore rank 0's bytes."""
+    import ctypes as C
+    from f5_tts_mlx_b200 import _lib
+    nccl = C.CDLL("libnccl.so.2")
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+
+    uid = UniqueId()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    t = torch.frombuffer(bytearray(bytes(uid.internal)), dtype=torch.uint8).clone().to(dev)
+    dist.broadcast(t, src=0)
+    C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    buf = model.packed.buffer.clone()
+    want = int(buf.to(torch.int64).sum().item())
+    if rank != 0:
+        buf.random_(0, 255)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = _lib.load().f5_nccl_broadcast_weights(C.c_void_p(buf.data_ptr()), buf.numel(), 0, comm, C.c_void_p(st))
+    torch.cuda.synchronize()
+    ok = rc == 0 and int(buf.to(torch.int64).sum().item()) == want and torch.equal(buf, model.packed.buffer)
+    oks = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    assert oks.item() == 1, "f5_nccl_broadcast_weights did not reproduce the root's packed weights"
+    return True
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -23,6 +59,7 @@ def main():
     model = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
                 text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev)
     load_weights_distributed(model, lambda: random_dit_weights(cfg, seed=1234))        # rank 0 packs, ONE broadcast
+    c_bcast = c_abi_broadcast_check(model, rank, world, dev)
     f5 = F5TTS(model)
     g = torch.Generator().manual_seed(77)
     B = 5                                                                              # 3 + 2 utterances
@@ -47,7 +84,7 @@ def main():
             bitwise = bitwise and torch.equal(outs[i], full[i])
         rel = max(((outs[i] - full[i]).norm() / full[i].norm()).item() for i in range(B))
         res = {"world": world, "utterances": B, "max_abs": max(diffs), "max_rel": rel, "bitwise_equal": bitwise,
-               "frames": int(full.shape[1])}
+               "frames": int(full.shape[1]), "c_abi_nccl_broadcast": c_bcast}
         print("NCCL_SHARD_CHECK " + json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -102,3 +102,79 @@ def test_header_is_plain_c99_and_links_from_c(tmp_path):
     assert "abi=" in r.stdout and "structs=10" in r.stdout
     if not torch.cuda.is_available():
         assert "device_check=-3" in r.stdout and "gemm_rc=-3" in r.stdout     # F5_ERR_NO_DEVICE, no CPU fallback
+
+
+# ---------------- host utilities for non-Python hosts (f5_pack_weights / f5_workspace_bytes) ----------------
+def _dims(cfg):
+    d = _lib.DitDims()
+    d.dim, d.depth, d.heads, d.ff_inner, d.mel_dim = cfg.dim, cfg.depth, cfg.heads, cfg.ff_inner, cfg.mel_dim
+    d.text_dim, d.conv_layers, d.text_num_embeds = cfg.text_dim, cfg.conv_layers, cfg.text_num_embeds
+    return d
+
+
+def test_c_weight_packer_matches_the_python_pack_byte_for_byte():
+    """f5_pack_weights (C, callback over MLX-named fp32 host tensors) produces the same packed buffer as
+    weights.PackedDiT.load: same layout, same fused / re-laid-out matrices, same bf16 rounding — except the text
+    position table, whose cos/sin come from libm instead of torch (compared to 1e-6)."""
+    import numpy as np
+    from f5_tts_mlx_b200.weights import DiTConfig, PackedDiT, random_dit_weights
+    lib = _lib.load()
+    cfg = DiTConfig(dim=256, depth=2, heads=4, text_num_embeds=40, text_dim=128, conv_layers=2)
+    W = random_dit_weights(cfg, seed=5)
+    ref = PackedDiT(cfg, "cpu").load(W)
+    d = _dims(cfg)
+    assert lib.f5_packed_weights_bytes(C.byref(d)) == ref.nbytes
+    keep = {k: v.detach().float().contiguous() for k, v in W.items()}
+    asked = []
+
+    @_lib.TENSOR_LOOKUP
+    def get(user, name, numel):
+        t = keep.get(name.decode())
+        asked.append(name.decode())
+        if t is None:
+            return None
+        numel[0] = t.numel()
+        return t.data_ptr()
+
+    out = torch.zeros(ref.nbytes, dtype=torch.uint8)
+    assert lib.f5_pack_weights(C.byref(d), get, None, C.c_void_p(out.data_ptr())) == 0, lib.f5_last_error()
+    pos = ref.specs["text_pos"]
+    n_pos = 4096 * cfg.text_dim * 4
+    mask = torch.ones(ref.nbytes, dtype=torch.bool); mask[pos.offset:pos.offset + n_pos] = False
+    assert torch.equal(out[mask], ref.buffer[mask])
+    a = out[pos.offset:pos.offset + n_pos].view(torch.float32); b = ref.buffer[pos.offset:pos.offset + n_pos].view(torch.float32)
+    assert (a - b).abs().max().item() < 1e-6
+    assert len(set(asked)) > 40
+    # a missing tensor is an error with the tensor's name in it, not a silent zero
+    del keep["transformer.proj_out.weight"]
+    assert lib.f5_pack_weights(C.byref(d), get, None, C.c_void_p(out.data_ptr())) == -1
+    assert b"transformer.proj_out.weight" in lib.f5_last_error()
+    # binding: every pointer of f5_dit_weights lands at the offset the Python side uses
+    from f5_tts_mlx_b200.weights import ConvNextWeightsC, DitBlockWeightsC, DitWeightsC
+    w = DitWeightsC(); tbs = (ConvNextWeightsC * cfg.conv_layers)(); blks = (DitBlockWeightsC * cfg.depth)()
+    base = 1 << 20
+    assert lib.f5_bind_packed_weights(C.byref(d), C.c_void_p(base), C.byref(w), tbs, blks) == 0
+    assert w.mod_w - base == ref.specs["mod_w"].offset and blks[1].ff2_w - base == ref.specs["blk1.ff2_w"].offset
+    assert tbs[1].grn_beta - base == ref.specs["tb1.grn_beta"].offset and w.proj_b - base == ref.specs["proj_b"].offset
+    assert w.ct_ld == ref.ct_ld and w.text_rows == cfg.text_num_embeds + 1
+
+
+def test_workspace_bytes_covers_the_python_session():
+    """f5_workspace_bytes >= the bytes dit.DitSession allocates for the same shape (each buffer 256-byte aligned)."""
+    from f5_tts_mlx_b200.weights import BASE_CONFIG
+    lib = _lib.load()
+    d = _dims(BASE_CONFIG)
+    s = _lib.DitShape()
+    s.batch, s.frames, s.cfg, s.n_times, s.text_len_max, s.masked, s.fused_adaln, s.bucketed = 1, 937, 1, 31, 152, 0, 1, 0
+    got = lib.f5_workspace_bytes(C.byref(d), C.byref(s))
+    D, F, Ct, R, T = 1024, 2048, 512, 2 * 937, 31
+    NM, ld = 22 * 6 * D + 2 * D, 22 * (3 * D + F) + 128
+    expect = (R * D * 4 * 3 + R * D * 2 * 2 + R * 3 * D * 2 + R * F * 2 + R * 100 * 4 + R * 128 * 2 + R * 640 * 2      # x,h,hoist / a,c / qkv / ff / v / y / ct
+              + R * Ct * 4 + R * Ct * 2 + 2 * R * 2 * Ct * 2 + 2 * 31 * 2 * Ct * 4                                       # text path
+              + T * NM * 4 + T * D * 2 + R * 16 * 2 * 4 + 4 * T * ld * 4 + 45 * 4 * T * D * 2                              # mod table, LN tables
+              + 152 * 4 + 2 * 4 + 937 * 100 * 4 + T * 4 + 937 * 64 * 4)
+    assert expect <= got <= expect + 40 * 256
+    s.fused_adaln = 0
+    assert lib.f5_workspace_bytes(C.byref(d), C.byref(s)) < got - 4 * T * ld * 4
+    s.batch = 0
+    assert lib.f5_workspace_bytes(C.byref(d), C.byref(s)) == -1

@@ -47,7 +47,8 @@ def launches():
     with open(os.path.join(PROF, f"{tag}_launch_shares.md"), "w") as f:
         f.write(f"# {tag}: launch list of `python bench.py --profile-run` under ncu (first {n} launches: precompute + "
                 "the first DiT evaluations of one step; cold-cache, serialised — compare SHARES)\n\n"
-                "command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv python bench.py --profile-run`\n\n"
+                "command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv python bench.py --profile-run` "
+                "(mel front-end + 2-point sample + Vocos first, then the bench step)\n\n"
                 "| kernel | launches | sum µs | avg µs | share |\n|---|---:|---:|---:|---:|\n")
         for k, (c, s) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {c} | {s:.1f} | {s / c:.2f} | {s / tot:.3f} |\n")
@@ -98,4 +99,32 @@ def benches():
             open(dst, "w").write(txt + "\n")
 
 
-launches(); fulls(); benches()
+def hbm_table():
+    """Achieved DRAM bandwidth of the HBM-bound kernels (prof_hbm capture) against the measured copy peak."""
+    rep = os.path.join(OUT, "prof_hbm.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    peak = 6583.5
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        peak = json.load(open(mp)).get("hbm_gbs", peak)
+    def num(v):
+        m = re.match(r"([0-9.,]+)\s*(\w*)", v or "0")
+        x = float(m.group(1).replace(",", ""))
+        return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "msecond": 1e-3}.get(m.group(2), 1)
+    agg = collections.OrderedDict()
+    for d in full(rep):
+        t = num(d.get("gpu__time_duration.sum")); by = num(d.get("dram__bytes_read.sum")) + num(d.get("dram__bytes_write.sum"))
+        a = agg.setdefault(d["kernel"] + " grid " + d["grid"], [0, 0.0, 0.0, d.get("lts__t_sector_hit_rate.pct", ""), d.get("sm__warps_active.avg.pct_of_peak_sustained_active", "")])
+        a[0] += 1; a[1] += t; a[2] += by
+    with open(os.path.join(PROF, f"{tag}_hbm_kernels.md"), "w") as f:
+        f.write(f"# {tag}: HBM / FFT kernels under `ncu --set full` (cold cache per replay): DRAM traffic per launch and achieved GB/s "
+                f"against the measured copy peak {peak:.0f} GB/s (MEASURED_PEAKS.json)\n\n"
+                "| kernel | launches | avg us | DRAM MB / launch | achieved GB/s | of peak | L2 hit % | warps active % |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, (n, t, by, hit, wa) in agg.items():
+            gbs = by / t / 1e9 if t > 0 else 0.0
+            f.write(f"| `{k}` | {n} | {t / n * 1e6:.2f} | {by / n / 1e6:.3f} | {gbs:.0f} | {gbs / peak:.3f} | {hit.split()[0] if hit else ''} | {wa.split()[0] if wa else ''} |\n")
+    print("hbm kernels:", len(agg))
+
+
+launches(); fulls(); hbm_table(); benches()
