@@ -105,6 +105,34 @@ struct Gemm2Smem {
   static_assert(kTotal <= 232448, "CTA-pair GEMM: shared memory over the 227 KB limit");
 };
 
+// Tile walk of one cluster: tiles t = first + i * stride, i < count, with t = m_tile * n_tiles + n_tile.
+// Default: first = cluster, stride = clusters (n-fastest round robin).  "Row-sticky" walk when there are more tiles
+// than clusters but no more row blocks than clusters and it costs no extra round (QKV at batch 1: 8 row blocks x 16
+// column tiles on 74 clusters): G = clusters / m_tiles clusters share one row block and split its column tiles, so a
+// cluster's tiles all have the SAME rows — the epilogue loads the rows' RoPE table / LayerNorm statistics once.
+struct TileWalk {
+  int first, stride, count;
+  bool sticky;
+};
+__device__ __forceinline__ TileWalk tile_walk(int cluster_id, int num_clusters, int n_tiles, int total_tiles) {
+  TileWalk w;
+  const int m_tiles = total_tiles / n_tiles;
+  const int G = m_tiles > 0 ? num_clusters / m_tiles : 0;
+  w.sticky = total_tiles > num_clusters && G >= 1 &&
+             (n_tiles + G - 1) / G <= (total_tiles + num_clusters - 1) / num_clusters;
+  if (w.sticky) {
+    const int m = cluster_id / G, j = cluster_id - m * G;
+    w.first = m * n_tiles + j;
+    w.stride = G;
+    w.count = (m < m_tiles && j < n_tiles) ? (n_tiles - j + G - 1) / G : 0;
+  } else {
+    w.first = cluster_id;
+    w.stride = num_clusters;
+    w.count = cluster_id < total_tiles ? (total_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+  }
+  return w;
+}
+
 template <int BN, bool OUT_BF16>
 struct Gemm2Lno {
   static constexpr bool value = !OUT_BF16 && BN == 256;
@@ -135,6 +163,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int kb_per_tap = (p.k_per_tap + 63) >> 6;
   const int num_kb = p.conv_taps * kb_per_tap;
   const int pair_tiles_per_batch = p.tiles_per_batch;   // in units of 256-row pair tiles
+  const TileWalk walk = tile_walk(cluster_id, num_clusters, n_tiles, total_tiles);
 
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 0);
   if (warp == 0 && lane == 0) {
@@ -163,9 +192,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 1);
   // first ring of B (weight) tiles of this cluster's first tile: requested before the PDL wait (gemm_sm100.cuh)
-  const int early_b = (p.w_static && cluster_id < total_tiles) ? min(kStages, num_kb) : 0;
+  const int early_b = (p.w_static && walk.count > 0) ? min(kStages, num_kb) : 0;
   if (warp == 0 && lane == 0) {
-    const int n0e = (cluster_id % n_tiles) * BN;
+    const int n0e = (walk.first % n_tiles) * BN;
     for (int kb = 0; kb < early_b; ++kb) {
       if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * S::kStageBytes);
       tma_load_2d_2sm(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * 64,
@@ -185,7 +214,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int kcount = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      for (int i = 0, t = walk.first; i < walk.count; ++i, t += walk.stride) {
         const int n_tile = t % n_tiles, m_tile = t / n_tiles;
         const int n0 = n_tile * BN;
         int batch = 0, m_in_batch0;
@@ -218,7 +247,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
       int kcount = 0, acount = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acount) {
+      for (int i = 0; i < walk.count; ++i, ++acount) {
         const int as = acount & 1;
         const uint32_t aph = (acount >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aph ^ 1);
@@ -258,7 +287,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int lg = warp & 3;
     const int r_in_tile = (int)rank * 128 + lg * 32 + lane;   // row inside the 256-row pair tile
     int acount = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acount) {
+    constexpr bool kHalves = ((BN / 64) % 2 == 1);   // odd unit count: the groups split every unit instead (gemm_epilogue.cuh)
+    float2 cs[ROPE ? 32 : 1];
+    float ln_mu_r = 0.f, ln_rstd = 1.f;
+    for (int i = 0, t = walk.first; i < walk.count; ++i, t += walk.stride, ++acount) {
       const int n_tile = t % n_tiles, m_tile = t / n_tiles;
       const int n0 = n_tile * BN;
       const int as = acount & 1;
@@ -287,22 +319,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       float* gate_s = bias_s + BN;
       float* aux_s = gate_s + BN;
       epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, aux_s);   // both groups write the same values
-      float ln_mu_r, ln_rstd;
-      epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
-      constexpr bool kHalves = ((BN / 64) % 2 == 1);   // odd unit count: the groups split every unit instead (gemm_epilogue.cuh)
-      float2 cs[ROPE ? 32 : 1];
       float4 res0[8];
-      if constexpr (kHalves) {
-        epi_load_rope_half<ROPE>(p, pos, cs, grp);
-      } else {
-        epi_load_rope<ROPE>(p, pos, cs);
-        epi_load_resid(p, row, n0 + grp * 64, row_ok, res0);
+      if (!walk.sticky || i == 0) {     // row-sticky walk: every tile of this cluster has the same rows
+        epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);
+        if constexpr (kHalves) epi_load_rope_half<ROPE>(p, pos, cs, grp);
+        else epi_load_rope<ROPE>(p, pos, cs);
       }
+      if constexpr (!kHalves) epi_load_resid(p, row, n0 + grp * 64, row_ok, res0);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 
       mbar_wait(&tmem_full_bar[as], aph);
       tc_fence_after();
-      if (t + num_clusters >= total_tiles) pdl_launch_dependents();   // last tile of this CTA: see gemm_sm100.cuh
+      if (i + 1 == walk.count) pdl_launch_dependents();   // last tile of this CTA: see gemm_sm100.cuh
       if (warp == 4 && lane == 0 && acount == 0) ts_mark(p, blockIdx.x, 7);
       EpiStage stg;
       stg.buf = smem + S::kStageOutOffset + grp * 32768;
@@ -336,7 +364,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
     }
-    if (et == 0) tma_store_wait<0>();   // this group's TMA stores have landed before the CTA retires
+    if (et == 0) tma_store_wait_read<0>();   // the staging buffers must outlive the TMA unit's reads; grid completion
+                                             // makes the global writes visible to the dependent kernel
     if (warp == 4 && lane == 0) ts_mark(p, blockIdx.x, 8);
   }
 

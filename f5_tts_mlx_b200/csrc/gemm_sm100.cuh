@@ -251,7 +251,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                  row_valid, stg, 0, 1);
       }
     }
-    if (et == 0) tma_store_wait<0>();   // this group's TMA stores have landed before the CTA retires
+    if (et == 0) tma_store_wait_read<0>();   // the staging buffers must outlive the TMA unit's reads; grid completion
+                                             // makes the global writes visible to the dependent kernel
     tc_fence_before();
     if (warp == 2 + 4 * (GemmEpi<BN, kStages>::kGroups - 1) && lane == 0) ts_mark(p, cta_lin, 8);
   }

@@ -125,3 +125,44 @@ def test_attention_handoff_barriers_are_balanced_and_order_the_groups(num_kv, mo
     assert pc == {0: num_kv, 1: num_kv}, "a group starved (deadlock)"
     assert pending == {2: 0, 3: 0}, "an arrive was left unconsumed at exit"
     assert order == [(g, j) for j in range(num_kv) for g in (0, 1)]   # strict alternation 0,1,0,1,...
+
+
+def _tile_walk(cluster_id, num_clusters, n_tiles, total_tiles):
+    """Python restatement of gemm2_sm100.cuh tile_walk()."""
+    m_tiles = total_tiles // n_tiles
+    G = num_clusters // m_tiles if m_tiles > 0 else 0
+    sticky = total_tiles > num_clusters and G >= 1 and -(-n_tiles // G) <= -(-total_tiles // num_clusters)
+    if sticky:
+        m, j = divmod(cluster_id, G)
+        first, stride = m * n_tiles + j, G
+        count = -(-(n_tiles - j) // G) if (m < m_tiles and j < n_tiles) else 0
+    else:
+        first, stride = cluster_id, num_clusters
+        count = -(-(total_tiles - cluster_id) // num_clusters) if cluster_id < total_tiles else 0
+    return first, stride, count, sticky
+
+
+def test_pair_gemm_tile_walk_covers_every_tile_once_and_row_sticky_keeps_rows():
+    """The persistent CTA-pair GEMM's tile walk: every tile exactly once for any (clusters, n_tiles, m_tiles); in the
+    row-sticky mode (QKV at batch 1: 8 x 16 tiles on 74 clusters) all tiles of a cluster share the row block and
+    no cluster gets more tiles than with the round-robin walk."""
+    seen_sticky = False
+    for clusters in (1, 2, 7, 64, 74):
+        for n_tiles in (1, 2, 4, 12, 16, 24):
+            for m_tiles in (1, 2, 8, 9, 75, 469):
+                total = n_tiles * m_tiles
+                launched = min(clusters, total)
+                tiles, per = [], []
+                for c in range(launched):
+                    first, stride, count, sticky = _tile_walk(c, launched, n_tiles, total)
+                    mine = [first + i * stride for i in range(count)]
+                    tiles += mine
+                    per.append(len(mine))
+                    if sticky:
+                        seen_sticky = True
+                        assert len({t // n_tiles for t in mine}) <= 1
+                assert sorted(tiles) == list(range(total)), (clusters, n_tiles, m_tiles)
+                assert max(per) <= -(-total // launched)
+    assert seen_sticky
+    first, stride, count, sticky = _tile_walk(10, 74, 16, 128)
+    assert sticky and (first, stride, count) == (1 * 16 + 1, 9, 2)
