@@ -66,6 +66,7 @@ class GemmArgs(C.Structure):
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("ln_scale", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_in_stats", C.c_void_p),
         ("ln_tab", C.c_void_p), ("ln_tab_ld", C.c_int64),
+        ("ab_fp8", C.c_int32), ("out2_fp8", C.c_int32), ("acc_scale", C.c_float), ("reserved_fp8", C.c_int32),
     ]
 
 

@@ -111,6 +111,14 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   F5_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "f5_gemm_bf16: bad shape m=%d n=%d k=%d", a->m,
              a->n, a->k);
   F5_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0, "f5_gemm_bf16: lda/ldw must be multiples of 8");
+  const bool ab8 = a->ab_fp8 != 0;
+  if (ab8) {
+    F5_REQUIRE(a->lda % 16 == 0 && a->ldw % 16 == 0 && a->k % 128 == 0 && a->acc_scale > 0.f,
+               "f5_gemm_bf16: FP8 mode needs lda/ldw %% 16 == 0, k %% 128 == 0 and acc_scale > 0");
+    F5_REQUIRE((a->conv_taps <= 1) && !a->conv_grouped, "f5_gemm_bf16: FP8 mode is for plain GEMMs");
+  }
+  const int esz = ab8 ? 1 : 2;       // operand element size
+  const uint32_t kbox = ab8 ? 128 : 64;
   F5_REQUIRE(a->n % (a->out_bf16 ? 8 : 4) == 0, "f5_gemm_bf16: n=%d not vector aligned", a->n);
   F5_REQUIRE(a->ldo % (a->out_bf16 ? 8 : 4) == 0, "f5_gemm_bf16: ldo not vector aligned");
   const int taps = a->conv_taps > 0 ? a->conv_taps : 1;
@@ -144,7 +152,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     if (int e = make_tmap_out(&to, a->out, a->out_bf16 ? 2 : 4, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo)) return e;
     if (a->out2_bf16) {
       F5_REQUIRE(!a->out_bf16, "f5_gemm_bf16: out2_bf16 needs an fp32 out");
-      if (int e = make_tmap_out(&to2, a->out2_bf16, 2, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo2)) return e;
+      if (int e = make_tmap_out(&to2, a->out2_bf16, a->out2_fp8 ? 1 : 2, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo2)) return e;
     } else {
       to2 = to;
     }
@@ -203,20 +211,21 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     p2.ln_scale = a->ln_scale; p2.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
     p2.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p2.ln_in_units = a->k / 64;
     p2.ln_tab = a->ln_tab; p2.ln_tab_ld = a->ln_tab_ld;
+    p2.ab8 = ab8 ? 1 : 0; p2.acc_scale = ab8 ? a->acc_scale : 1.f; p2.out2_fp8 = a->out2_fp8;
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
     {
       uint64_t dims[3] = {(uint64_t)a->k, (uint64_t)(batched ? rpb : a->m), (uint64_t)(batched ? nb : 1)};
-      uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * (uint64_t)rpb};
-      uint32_t box[3] = {64, 128, 1};
-      if (int e = make_tmap_bf16(&ta2, a->a, 3, dims, str, box)) return e;
+      uint64_t str[2] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * (uint64_t)rpb};
+      uint32_t box[3] = {kbox, 128, 1};
+      if (int e = (ab8 ? make_tmap_u8 : make_tmap_bf16)(&ta2, a->a, 3, dims, str, box)) return e;
     }
     {
       const int kpad = cdiv(a->k, 64) * 64;
       uint64_t dims[2] = {(uint64_t)(taps == 1 ? a->k : taps * kpad), (uint64_t)a->n};
-      uint64_t str[1] = {(uint64_t)a->ldw * 2};
-      uint32_t box[2] = {64, (uint32_t)(bn2 / 2)};
-      if (int e = make_tmap_bf16(&tb2, a->w, 2, dims, str, box)) return e;
+      uint64_t str[1] = {(uint64_t)a->ldw * esz};
+      uint32_t box[2] = {kbox, (uint32_t)(bn2 / 2)};
+      if (int e = (ab8 ? make_tmap_u8 : make_tmap_bf16)(&tb2, a->w, 2, dims, str, box)) return e;
     }
     const int n_tiles = cdiv(a->n, bn2);
     const int m_tiles = batched ? nb * cdiv(rpb, 256) : cdiv(a->m, 256);
@@ -265,6 +274,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   p.ln_scale = a->ln_scale; p.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
   p.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p.ln_in_units = a->k / 64;
   p.ln_tab = a->ln_tab; p.ln_tab_ld = a->ln_tab_ld;
+  p.ab8 = ab8 ? 1 : 0; p.acc_scale = ab8 ? a->acc_scale : 1.f; p.out2_fp8 = a->out2_fp8;
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows
@@ -273,16 +283,16 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     const int kcols = a->conv_grouped ? a->n : a->k;  // grouped: channel axis spans all groups
     uint64_t dims[3] = {(uint64_t)kcols, (uint64_t)(batched ? rpb : a->m),
                         (uint64_t)(batched ? nb : 1)};
-    uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * (uint64_t)rpb};
-    uint32_t box[3] = {64, 128, 1};
-    if (int e = make_tmap_bf16(&ta, a->a, 3, dims, str, box)) return e;
+    uint64_t str[2] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * (uint64_t)rpb};
+    uint32_t box[3] = {kbox, 128, 1};
+    if (int e = (ab8 ? make_tmap_u8 : make_tmap_bf16)(&ta, a->a, 3, dims, str, box)) return e;
   }
   {
     const int kpad = cdiv(a->k, 64) * 64;
     uint64_t dims[2] = {(uint64_t)(taps == 1 ? a->k : taps * kpad), (uint64_t)a->n};
-    uint64_t str[1] = {(uint64_t)a->ldw * 2};
-    uint32_t box[2] = {64, (uint32_t)bn};
-    if (int e = make_tmap_bf16(&tb, a->w, 2, dims, str, box)) return e;
+    uint64_t str[1] = {(uint64_t)a->ldw * esz};
+    uint32_t box[2] = {kbox, (uint32_t)bn};
+    if (int e = (ab8 ? make_tmap_u8 : make_tmap_bf16)(&tb, a->w, 2, dims, str, box)) return e;
   }
   dim3 grid(cdiv(a->n, bn), batched ? nb * cdiv(rpb, 128) : cdiv(a->m, 128), 1);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -47,6 +47,15 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+__device__ __forceinline__ void umma_f8_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                 uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -98,8 +107,11 @@ struct Gemm2Smem {
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kColVecs = 3;
-  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;   // 2 stages x (bias_s[BN], gate_s[BN], aux_s[BN])
-  static constexpr int kStageOutOffset = (kColsOffset + 2 * kColVecs * BN * 4 + 1023) & ~1023;   // 2 x 16 KB store staging per group
+  // column vectors (bias_s[BN], gate_s[BN], aux_s[BN]): one copy per epilogue group and accumulator stage — the groups
+  // run tiles at their own pace, so a shared copy could be restaged by one group while the other still reads the
+  // previous tile's values (compute-sanitizer racecheck, r02)
+  static constexpr int kColsOffset = (kBarOffset + kNumBars * 8 + 16 + 15) & ~15;
+  static constexpr int kStageOutOffset = (kColsOffset + 2 * 2 * kColVecs * BN * 4 + 1023) & ~1023;   // 2 x 16 KB store staging per group
   static constexpr int kStage2Offset = kStageOutOffset + 2 * 32768;                  // 8 KB per group (LNO)
   static constexpr int kTotal = kStage2Offset + (LNO ? 2 * 8192 : 0) + 1024;  // + align slack
   static_assert(kTotal <= 232448, "CTA-pair GEMM: shared memory over the 227 KB limit");
@@ -160,7 +172,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int kb_per_tap = (p.k_per_tap + 63) >> 6;
+  const int kbe = p.ab8 ? 128 : 64;      // elements per k-block: always 128 bytes per row (one swizzle span)
+  const int kb_per_tap = (p.k_per_tap + kbe - 1) / kbe;
   const int num_kb = p.conv_taps * kb_per_tap;
   const int pair_tiles_per_batch = p.tiles_per_batch;   // in units of 256-row pair tiles
   const TileWalk walk = tile_walk(cluster_id, num_clusters, n_tiles, total_tiles);
@@ -197,7 +210,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     const int n0e = (walk.first % n_tiles) * BN;
     for (int kb = 0; kb < early_b; ++kb) {
       if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * S::kStageBytes);
-      tma_load_2d_2sm(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * 64,
+      tma_load_2d_2sm(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * kbe,
                       n0e + (int)rank * (BN / 2));
     }
   }
@@ -234,9 +247,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           if (rank == 0 && !early) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
           const int tap = kb / kb_per_tap;
           const int kc = kb - tap * kb_per_tap;
-          const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
+          const int a_col = (p.conv_grouped ? n0 : 0) + kc * kbe;
           tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
-          if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * 64, n0 + (int)rank * (BN / 2));
+          if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * kbe, n0 + (int)rank * (BN / 2));
           if (kcount == 0) ts_mark(p, blockIdx.x, 3);
         }
       }
@@ -246,6 +259,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc8 = umma_idesc_e4m3(256, BN);
+      const bool ab8 = p.ab8 != 0;
       int kcount = 0, acount = 0;
       for (int i = 0; i < walk.count; ++i, ++acount) {
         const int as = acount & 1;
@@ -266,7 +281,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
             for (int k = 0; k < 4; ++k) {
               uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
               uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-              umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+              if (ab8) umma_f8_ss_2sm(tmem_acc, da, db, idesc8, (kb | k) != 0);
+              else umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
             }
             tc_commit_2sm(&empty_bar[s], 3);
             if (kb == num_kb - 1) tc_commit_2sm(&tmem_full_bar[as], 3);
@@ -315,10 +331,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       if (p.row_len != nullptr) row_valid = pos < p.row_len[b_idx];
 
       // operand staging for this tile (overlaps the MMAs still filling the accumulator)
-      float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + as * S::kColVecs * BN;
+      float* bias_s = reinterpret_cast<float*>(smem + S::kColsOffset) + (grp * 2 + as) * S::kColVecs * BN;
       float* gate_s = bias_s + BN;
       float* aux_s = gate_s + BN;
-      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, aux_s);   // both groups write the same values
+      epi_stage_cols<BN>(p, n0, et, bias_s, gate_s, aux_s);   // this group's own copy
       float4 res0[8];
       if (!walk.sticky || i == 0) {     // row-sticky walk: every tile of this cluster has the same rows
         epi_load_ln_row(p, row, row_ok, ln_mu_r, ln_rstd);

@@ -53,6 +53,10 @@ struct GemmParams {
   int ln_in_units;            // K/64
   const float* ln_tab;        // 4 rows of ln_tab_ld floats: c1_hi, c1_lo, c2_hi, c2_lo (bf16-split operand rows of
   long long ln_tab_ld;        //   the table GEMM), already offset to this GEMM's column 0
+  // ---- FP8 mode of the block GEMMs ----
+  int ab8;                 // A and W are e4m3 bytes: 128-element k-blocks, kind::f8f6f4 MMAs
+  float acc_scale;         // multiplies the accumulator (the weight tensor's quantisation scale); 1 otherwise
+  int out2_fp8;            // the second output is e4m3 (1 byte per element) instead of bf16
 };
 
 // Each CTA touches its 1/num_ctas slice of [pf_ptr, pf_ptr + pf_bytes) with L2 prefetches (one warp,
@@ -209,9 +213,10 @@ struct EpiStage {
 };
 
 // `w2`: the chunk's second output (bf16, 4 x uint4 per row) or nullptr
+// `w2_fp8`: the second output is e4m3 — 32-byte rows, SWIZZLE_32B (16-byte chunk index ^ bit 7 of the row offset)
 template <bool OUT_BF16>
 __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiStage& st, int par, int col0,
-                                              const uint4* w2 = nullptr) {
+                                              const uint4* w2 = nullptr, bool w2_fp8 = false) {
   uint8_t* buf = st.buf + par * 16384;
   uint8_t* buf2 = st.buf2 + par * st.buf2_par;
 #if F5_EPI_WAIT_MODE == 1
@@ -242,10 +247,17 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
       *reinterpret_cast<float4*>(mine + ((j ^ sw) * 16)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
   if (w2 != nullptr) {
-    uint8_t* mine2 = buf2 + st.r * 64;
-    const int sw2 = (st.r >> 1) & 3;
+    if (w2_fp8) {
+      uint8_t* mine2 = buf2 + st.r * 32;
+      const int sw2 = (st.r >> 2) & 1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
+      for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
+    } else {
+      uint8_t* mine2 = buf2 + st.r * 64;
+      const int sw2 = (st.r >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(mine2 + ((j ^ sw2) * 16)) = w2[j];
+    }
   }
   fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA unit
 #if F5_EPI_WAIT_MODE != 1
@@ -271,15 +283,17 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
                                           int col0, int row, int b_idx, bool row_ok, bool row_valid,
                                           const EpiStage& st, float2& unit_acc) {
   float v[32];
-  // rstd * acc - (mean * rstd) * c1 + (c2 + bias): the fused-LN consumer; (mu_r, rstd) = (0, 1) otherwise
+  // rstd * acc - (mean * rstd) * c1 + (c2 + bias): the fused-LN consumer; (mu_r, rstd) = (0, 1) otherwise.
+  // acc_scale (the e4m3 weight tensor's scale in FP8 mode, else 1) belongs to the accumulator term only.
+  const float ra = st.rstd * p.acc_scale;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
     const float4 cc = *reinterpret_cast<const float4*>(aux_s + j);
-    v[j] = fmaf(__uint_as_float(acc[j]), st.rstd, fmaf(-st.mu_r, cc.x, bb.x));
-    v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), st.rstd, fmaf(-st.mu_r, cc.y, bb.y));
-    v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), st.rstd, fmaf(-st.mu_r, cc.z, bb.z));
-    v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), st.rstd, fmaf(-st.mu_r, cc.w, bb.w));
+    v[j] = fmaf(__uint_as_float(acc[j]), ra, fmaf(-st.mu_r, cc.x, bb.x));
+    v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), ra, fmaf(-st.mu_r, cc.y, bb.y));
+    v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), ra, fmaf(-st.mu_r, cc.z, bb.z));
+    v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), ra, fmaf(-st.mu_r, cc.w, bb.w));
   }
   if (ACT == ACT_GELU_TANH) {
 #pragma unroll
@@ -340,14 +354,28 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
         if (HALF == 1 && row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 6) + (col0 >> 6)] = unit_acc;
       }
       uint4 w2[4];
+      if (p.out2_fp8) {      // e4m3 operand of an FP8-mode consumer: 32 bytes per row and chunk
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 s0 = *reinterpret_cast<const float4*>(aux_s + 8 * j);
-        const float4 s1 = *reinterpret_cast<const float4*>(aux_s + 8 * j + 4);
-        w2[j] = make_uint4(pack_bf16x2(v[8 * j] * s0.x, v[8 * j + 1] * s0.y), pack_bf16x2(v[8 * j + 2] * s0.z, v[8 * j + 3] * s0.w),
-                           pack_bf16x2(v[8 * j + 4] * s1.x, v[8 * j + 5] * s1.y), pack_bf16x2(v[8 * j + 6] * s1.z, v[8 * j + 7] * s1.w));
+        for (int j = 0; j < 2; ++j) {
+          uint32_t q[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 sc = *reinterpret_cast<const float4*>(aux_s + 16 * j + 4 * i);
+            q[i] = pack_e4m3x4(v[16 * j + 4 * i] * sc.x, v[16 * j + 4 * i + 1] * sc.y, v[16 * j + 4 * i + 2] * sc.z,
+                               v[16 * j + 4 * i + 3] * sc.w);
+          }
+          w2[j] = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 s0 = *reinterpret_cast<const float4*>(aux_s + 8 * j);
+          const float4 s1 = *reinterpret_cast<const float4*>(aux_s + 8 * j + 4);
+          w2[j] = make_uint4(pack_bf16x2(v[8 * j] * s0.x, v[8 * j + 1] * s0.y), pack_bf16x2(v[8 * j + 2] * s0.z, v[8 * j + 3] * s0.w),
+                             pack_bf16x2(v[8 * j + 4] * s1.x, v[8 * j + 5] * s1.y), pack_bf16x2(v[8 * j + 6] * s1.z, v[8 * j + 7] * s1.w));
+        }
       }
-      epi_store_tma<OUT_BF16>(v, st, st.par_base ^ HALF, col0, w2);
+      epi_store_tma<OUT_BF16>(v, st, st.par_base ^ HALF, col0, w2, p.out2_fp8 != 0);
       return;
     }
   }

@@ -84,7 +84,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     row0 = blockIdx.y * 128;
     m_in_batch0 = row0;
   }
-  const int kb_per_tap = (p.k_per_tap + 63) >> 6;
+  const int kbe = p.ab8 ? 128 : 64;      // elements per k-block: always 128 bytes per row (one swizzle span)
+  const int kb_per_tap = (p.k_per_tap + kbe - 1) / kbe;
   const int num_kb = p.conv_taps * kb_per_tap;
 
   // ---- one-time setup (overlaps the predecessor kernel under PDL) ----
@@ -118,7 +119,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0 && lane == 0) {
     for (int kb = 0; kb < early_b; ++kb) {
       mbar_expect_tx(&full_bar[kb], S::kStageBytes);
-      tma_load_2d(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * 64, n0);
+      tma_load_2d(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * kbe, n0);
     }
   }
   pdl_wait();   // predecessor's outputs (our A operand / residual) are complete and visible
@@ -136,10 +137,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (kb >= early_b) mbar_expect_tx(&full_bar[s], S::kStageBytes);
         const int tap = kb / kb_per_tap;
         const int kc = kb - tap * kb_per_tap;
-        const int a_col = (p.conv_grouped ? n0 : 0) + kc * 64;
+        const int a_col = (p.conv_grouped ? n0 : 0) + kc * kbe;
         tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
                     p.tiles_per_batch > 0 ? batch : 0);
-        if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * 64, n0);
+        if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * kbe, n0);
 #ifndef F5_EPI_PROBE
         if (kb == 0) ts_mark(p, cta_lin, 3);
 #endif
@@ -151,6 +152,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint32_t idesc8 = umma_idesc_e4m3(128, BN);
+    const bool ab8 = p.ab8 != 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (kb / kStages) & 1;
@@ -164,7 +167,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) per 64-wide k-block; +32 B per step
           uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
           uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-          umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+          if (ab8) umma_f8_ss(tmem_base, da, db, idesc8, (kb | k) != 0);   // 32 e4m3 per instruction = the same 32 bytes
+          else umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         tc_commit(&empty_bar[s]);                        // frees the smem slot when MMAs retire
         if (kb == num_kb - 1) {

@@ -78,8 +78,18 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int make_tmap_any(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dt);
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_any(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+int make_tmap_u8(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_any(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_UINT8);
+}
+static int make_tmap_any(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dt) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(F5_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[5];
@@ -98,7 +108,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
     if (gstr[i] % 16 != 0)
       return set_error(F5_ERR_INVALID, "TMA stride %d = %llu bytes not a multiple of 16", i,
                        (unsigned long long)gstr[i]);
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -120,9 +130,13 @@ int make_tmap_out(CUtensorMap* map, const void* base, int elem_bytes, uint64_t c
   cuuint64_t gstr[2] = {ld_elems * elem_bytes, ld_elems * elem_bytes * rows};
   cuuint32_t bx[3] = {32, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+  const CUtensorMapDataType odt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                  : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+  const CUtensorMapSwizzle osw = elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(map, odt, 3,
                    const_cast<void*>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   osw,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(F5_ERR_CUDA, "cuTensorMapEncodeTiled (output map) failed with CUresult %d", (int)r);

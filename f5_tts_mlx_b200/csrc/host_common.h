@@ -33,8 +33,12 @@ int device_check();
 // strides in BYTES for dims 1.. (rank-1 entries).  Returns 0 or error.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// the same for 1-byte elements (e4m3 operands of the FP8 mode): 128-byte swizzle, box[0] = 128 elements
+int make_tmap_u8(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box);
 // Tensor map of an OUTPUT matrix for the GEMM epilogue's TMA stores: elem_bytes 4 (fp32, 32-column boxes = 128 B rows,
-// 128-byte swizzle) or 2 (bf16, 32-column boxes = 64 B rows, 64-byte swizzle); dims (cols, rows per utterance, utterances).
+// 128-byte swizzle), 2 (bf16, 32-column boxes = 64 B rows, 64-byte swizzle) or 1 (e4m3, 32 B rows, 32-byte swizzle);
+// dims (cols, rows per utterance, utterances).
 int make_tmap_out(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t batches,
                   uint64_t ld_elems);
 

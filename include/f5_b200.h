@@ -123,6 +123,15 @@ typedef struct f5_gemm_args {
   const float* ln_in_stats;
   const float* ln_tab;
   int64_t ln_tab_ld;
+  /* FP8 mode (the B200 analogue of the reference's quantised `--q` checkpoints, cfm.py:451-452,510-515): with ab_fp8
+   * both `a` and `w` hold e4m3 bytes (lda / ldw in elements = bytes, multiples of 16; k a multiple of 128) and the
+   * accumulator is multiplied by acc_scale (the weight tensor's quantisation scale, > 0) before bias / LN terms;
+   * with out2_fp8 the second output out2_bf16 is written as e4m3 bytes (ldo2 in bytes) — the A operand of the next
+   * FP8-mode GEMM.  Both 0 = bf16 everywhere. */
+  int32_t ab_fp8;
+  int32_t out2_fp8;
+  float acc_scale;
+  int32_t reserved_fp8;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
