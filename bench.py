@@ -66,7 +66,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,clocks.mem,clocks.max.mem")
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.idx = [], None, gpu_index
@@ -88,17 +88,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, mem, pw = [], [], set(), [], []
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
+            try:
+                pw.append(float(r[3])); mem.append(float(r[8]))
+            except Exception:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "mem_mhz": statistics.median(mem) if mem else None,
+                "power_w": statistics.median(pw) if pw else None}
 
 
 def ncu_traffic() -> dict:
@@ -379,7 +384,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     cfg = BASE_CONFIG
     model = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
                 text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev,
-                fused_adaln=not args.no_fused_adaln)
+                fused_adaln=not args.no_fused_adaln, fp8=args.fp8)
     # rank 0 builds + packs the weights; ONE broadcast of the packed buffer (the only collective)
     if rank == 0:
         model.load_weights(random_dit_weights(cfg, seed=1234))
@@ -463,6 +468,25 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         subs["cfg3_b64_midpoint"]["note"] = (f"global batch {64 * world} utterances over {world} GPU(s); at --gpus 8 this is "
                                              "BASELINE config 4 (512 utterances sharded 64 per GPU)")
         f5._plans.clear(); model._sessions.clear(); torch.cuda.empty_cache()
+        if not args.fp8:
+            # the headline workload in FP8 mode (e4m3 operands on the four GEMMs of every block): the lossy analogue of
+            # the reference's quantised `--q` checkpoints, reported beside the bf16 headline, never instead of it
+            m8 = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
+                     text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev, fp8=True)
+            if rank == 0:
+                m8.load_weights(random_dit_weights(cfg, seed=1234))
+            else:
+                m8.allocate_weights()
+            if world > 1:
+                m8.packed.broadcast(src=0)
+            r = measure(F5TTS(m8), lib, Workload("b1_fp8", B, N, NR, args.method, args.ode_steps, args.cfg), rank, world, dev,
+                        max(3, min(args.steps, 10)), 3)
+            r.pop("_inputs")
+            r["dtype"] = "fp8 (e4m3 operands of QKV / out / FF1 / FF2, fp32 accumulate) + bf16 elsewhere"
+            r["note"] = "lossy mode: oracle-emulated drift 2.9e-2 per forward vs 3.9e-3 for bf16 (DESIGN.md section 8)"
+            subs["b1_fp8"] = r
+            del m8
+            torch.cuda.empty_cache()
 
     if rank != 0:
         return
@@ -480,7 +504,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                        "tests/mlx_shim (MLX itself is not installable in this image)"}
     line = {"metric": "mel-frames/sec", "value": m["value"], "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp8(e4m3 QKV/FF1)+bf16" if args.fp8 else "bf16", "data": "synthetic",
             "config": m["config"], "clocks": m.get("clocks"),
             "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": path, "ms_per_step": 1e3 * te.item() / e2e_steps, "batch": B},
@@ -506,6 +530,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the config-3 / config-5 sub-results")
     ap.add_argument("--no-fused-adaln", action="store_true", help="A/B: separate LayerNorm+modulate launches (r01 path)")
+    ap.add_argument("--fp8", action="store_true", help="FP8 mode (e4m3 QKV / FF1 GEMMs): the lossy analogue of the reference's --q; "
+                                                        "NOT the headline (dtype is reported as fp8+bf16)")
     ap.add_argument("--profile-run", action="store_true", help="one eager step and exit (for ncu)")
     args = ap.parse_args()
 

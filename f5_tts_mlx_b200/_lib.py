@@ -66,7 +66,7 @@ class GemmArgs(C.Structure):
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_int64),
         ("ln_scale", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_in_stats", C.c_void_p),
         ("ln_tab", C.c_void_p), ("ln_tab_ld", C.c_int64),
-        ("ab_fp8", C.c_int32), ("out2_fp8", C.c_int32), ("acc_scale", C.c_float), ("reserved_fp8", C.c_int32),
+        ("ab_fp8", C.c_int32), ("out2_fp8", C.c_int32), ("acc_scale", C.c_float), ("out_fp8", C.c_int32),
     ]
 
 
@@ -99,6 +99,8 @@ SYMBOLS: dict[str, tuple] = {
     "f5_debug_attention_ts": (C.c_int, [C.c_void_p]),
     "f5_attention_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "f5_attention_fwd_e4m3": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "f5_ln_modulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "f5_dwconv7_ln": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -11,16 +11,30 @@ extern "C" int f5_debug_attention_ts(void* base) {
   return 0;
 }
 
+static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch, int32_t frames,
+                          int32_t heads, int32_t head_dim, const int32_t* kv_len, int out_fp8, void* stream_);
+
 extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
                                 int32_t batch, int32_t frames, int32_t heads, int32_t head_dim,
                                 const int32_t* kv_len, void* stream_) {
+  return attention_impl(qkv, ld_qkv, out, ld_out, batch, frames, heads, head_dim, kv_len, 0, stream_);
+}
+// the same attention with an e4m3 output (ld_out in bytes): FP8 mode, the out-projection's A operand
+extern "C" int f5_attention_fwd_e4m3(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out,
+                                     int32_t batch, int32_t frames, int32_t heads, int32_t head_dim,
+                                     const int32_t* kv_len, void* stream_) {
+  return attention_impl(qkv, ld_qkv, out, ld_out, batch, frames, heads, head_dim, kv_len, 1, stream_);
+}
+
+static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch, int32_t frames,
+                          int32_t heads, int32_t head_dim, const int32_t* kv_len, int out_fp8, void* stream_) {
   using namespace f5;
   if (int e = device_check()) return e;
   F5_REQUIRE(qkv && out, "f5_attention_fwd: null pointer");
   F5_REQUIRE(head_dim == 64, "f5_attention_fwd: head_dim %d unsupported (only 64)", head_dim);
   F5_REQUIRE(batch > 0 && frames > 0 && heads > 0, "f5_attention_fwd: bad shape");
   F5_REQUIRE(ld_qkv % 8 == 0 && ld_qkv >= 3 * heads * 64, "f5_attention_fwd: bad ld_qkv");
-  F5_REQUIRE(ld_out % 8 == 0 && ld_out >= heads * 64, "f5_attention_fwd: bad ld_out");
+  F5_REQUIRE(ld_out % (out_fp8 ? 16 : 8) == 0 && ld_out >= heads * 64, "f5_attention_fwd: bad ld_out");
   CUtensorMap tm;
   uint64_t dims[3] = {(uint64_t)3 * heads * 64, (uint64_t)frames, (uint64_t)batch};
   uint64_t str[2] = {(uint64_t)ld_qkv * 2, (uint64_t)ld_qkv * 2 * (uint64_t)frames};
@@ -47,6 +61,8 @@ extern "C" int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int6
   }
   p.handoff = handoff;
   p.ts = g_attn_ts;
+  p.out_fp8 = out_fp8;
+  F5_REQUIRE(!out_fp8 || variant == 4, "f5_attention_fwd_e4m3: only the default kernel variant writes e4m3");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
                2.0 * batch * (double)frames * heads * 64.0 * 4.0, stream);

@@ -351,7 +351,18 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         uint32_t ov[32];
         tmem_ld32(tmem_O + c * 32, ov);
         tmem_wait_ld();
-        if (n < p.N) {
+        if (n < p.N && p.out_fp8) {
+          uint8_t* o8 = reinterpret_cast<uint8_t*>(p.out) + ((size_t)b * p.N + n) * p.ldo + h * 64 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 16) {
+            uint4 w;
+            w.x = pack_e4m3x4(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv, __uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+            w.y = pack_e4m3x4(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv, __uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+            w.z = pack_e4m3x4(__uint_as_float(ov[i + 8]) * inv, __uint_as_float(ov[i + 9]) * inv, __uint_as_float(ov[i + 10]) * inv, __uint_as_float(ov[i + 11]) * inv);
+            w.w = pack_e4m3x4(__uint_as_float(ov[i + 12]) * inv, __uint_as_float(ov[i + 13]) * inv, __uint_as_float(ov[i + 14]) * inv, __uint_as_float(ov[i + 15]) * inv);
+            *reinterpret_cast<uint4*>(o8 + i) = w;
+          }
+        } else if (n < p.N) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 w;

@@ -30,6 +30,7 @@ struct AttnParams {
   unsigned long long* ts;  // debug: [3 roles][64 tiles][8 slots] SM-clock stamps of CTA (0,0,0), or null
   int handoff;             // v2: softmax groups alternate in the exponential loop (F5_ATTN_HANDOFF=0 disables)
   unsigned long long* prof;  // in-graph timing slot (ptx.cuh prof_stamp_*), or null
+  int out_fp8;             // v2: `out` receives e4m3 bytes (ldo in bytes) — the A operand of an FP8-mode out-projection
 };
 
 struct AttnSmem {

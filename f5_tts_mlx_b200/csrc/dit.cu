@@ -14,6 +14,8 @@
 
 extern "C" int f5_attention_fwd(const void*, int64_t, void*, int64_t, int32_t, int32_t, int32_t,
                                 int32_t, const int32_t*, void*);
+extern "C" int f5_attention_fwd_e4m3(const void*, int64_t, void*, int64_t, int32_t, int32_t, int32_t,
+                                     int32_t, const int32_t*, void*);
 
 namespace f5 {
 
@@ -167,6 +169,13 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
   if (pf_env < 0) { const char* v = getenv("F5_PREFETCH"); pf_env = (v && v[0] == '0') ? 0 : 1; }
   const bool prefetch = pf_env && R <= 16384;
   const bool fused = ln_fused(b);
+  // FP8 mode of the QKV / FF1 GEMMs: e4m3 operand written by the producing epilogue, e4m3 weights (per-tensor scale)
+  const bool fp8 = fused && b->a_fp8 != nullptr && w->blocks[0].qkv_w8 != nullptr && w->blocks[0].ff1_w8 != nullptr;
+  // ... and of the out-projection / FF2 (A = attention output / GELU output, written as e4m3 by their producers into the
+  // first half of the bf16 buffers); F5_FP8_LEVEL=1 keeps those two in bf16 (A/B measurements)
+  static int fp8_level = -1;
+  if (fp8_level < 0) { const char* v = getenv("F5_FP8_LEVEL"); fp8_level = (v && v[0] == '1') ? 1 : 2; }
+  const bool fp8b = fp8 && fp8_level >= 2 && w->blocks[0].out_w8 != nullptr && w->blocks[0].ff2_w8 != nullptr;
   static const GemmTune t_qkv = tune_of("qkv"), t_out = tune_of("out"), t_ff1 = tune_of("ff1"), t_ff2 = tune_of("ff2");
   const long long tab_ld = ln_tab_ld(w);
   const float* tab = fused ? b->ln_tab + (size_t)4 * ti * tab_ld : nullptr;   // this time's 4 operand rows
@@ -196,7 +205,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
     g.resid = b->h; g.ldr = D;
     if (fused) {   // the stream's first producer: operand + statistics for block 0's attn_norm
       g.ln_scale = (w->depth > 0 ? mod + D : mod + (size_t)w->depth * 6 * D); g.ln_stats = b->ln_stats;
-      g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+      g.out2_bf16 = fp8 ? b->a_fp8 : b->a_bf16; g.ldo2 = D; g.out2_fp8 = fp8 ? 1 : 0;
     }
     if (int e = f5_gemm_bf16(&g, st)) return e;
   }
@@ -211,6 +220,7 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.qkv_w, D, R, 3 * D, D, b->qkv_bf16, 3 * D, true);
       g.bias = bw.qkv_b;
       if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F); g.ln_tab_ld = tab_ld; }
+      if (fp8) { g.a = b->a_fp8; g.w = bw.qkv_w8; g.ab_fp8 = 1; g.acc_scale = bw.qkv_s8; }
       g.variant = t_qkv.variant; g.tile_n = t_qkv.tile_n;
       g.rows_per_batch = N; g.num_batches = BU;
       g.rope = b->rope; g.rope_cols = 2 * D; g.q_scale = 0.125f; g.q_cols = D;
@@ -218,8 +228,8 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       if (prefetch) { g.prefetch = bw.out_w; g.prefetch_bytes = (int64_t)2 * D * D; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
-    if (int e = f5_attention_fwd(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64,
-                                 b->seq_len ? b->seq_len : b->valid_len, st))
+    if (int e = (fp8b ? f5_attention_fwd_e4m3 : f5_attention_fwd)(b->qkv_bf16, 3 * D, b->c_bf16, D, BU, N, w->heads, 64,
+                                                                  b->seq_len ? b->seq_len : b->valid_len, st))
       return e;
     {
       f5_gemm_args g = gemm_base(b->c_bf16, D, bw.out_w, D, R, D, D, b->x, D, false);
@@ -228,7 +238,11 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       g.gate = m + 2 * D; g.gate_ld = 0;
       g.resid = b->x; g.ldr = D;
       if (prefetch) { g.prefetch = bw.ff1_w; g.prefetch_bytes = (int64_t)2 * F * D; }
-      if (fused) { g.ln_scale = m + 4 * D; g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D; }   // ff_norm
+      if (fused) {   // ff_norm
+        g.ln_scale = m + 4 * D; g.ln_stats = b->ln_stats;
+        g.out2_bf16 = fp8 ? b->a_fp8 : b->a_bf16; g.ldo2 = D; g.out2_fp8 = fp8 ? 1 : 0;
+      }
+      if (fp8b) { g.w = bw.out_w8; g.ab_fp8 = 1; g.acc_scale = bw.out_s8; }     // A = c_bf16's bytes, e4m3 [R, D]
       g.variant = t_out.variant; g.tile_n = t_out.tile_n;
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }
@@ -238,6 +252,8 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       f5_gemm_args g = gemm_base(b->a_bf16, D, bw.ff1_w, D, R, F, D, b->ff_bf16, F, true);
       g.bias = bw.ff1_b; g.act = F5_ACT_GELU_TANH;
       if (fused) { g.ln_in_stats = b->ln_stats; g.ln_tab = tab + (size_t)l * (3 * D + F) + 3 * D; g.ln_tab_ld = tab_ld; }
+      if (fp8) { g.a = b->a_fp8; g.w = bw.ff1_w8; g.ab_fp8 = 1; g.acc_scale = bw.ff1_s8; }
+      if (fp8b) g.out_fp8 = 1;                                                   // ff_bf16's bytes as e4m3 [R, F]
       g.variant = t_ff1.variant; g.tile_n = t_ff1.tile_n;
       if (prefetch) { g.prefetch = bw.ff2_w; g.prefetch_bytes = (int64_t)2 * D * F; }
       if (int e = f5_gemm_bf16(&g, st)) return e;
@@ -254,7 +270,9 @@ extern "C" int f5_dit_forward(const f5_dit_weights* w, const f5_dit_buffers* b, 
       if (fused) {   // next block's attn_norm scale, or norm_out's (scale first, dit.py:287)
         g.ln_scale = (l + 1 < w->depth) ? mod + (size_t)(l + 1) * 6 * D + D : mod + (size_t)w->depth * 6 * D;
         g.ln_stats = b->ln_stats; g.out2_bf16 = b->a_bf16; g.ldo2 = D;
+        if (fp8 && l + 1 < w->depth) { g.out2_bf16 = b->a_fp8; g.out2_fp8 = 1; }   // proj_out (after the last block) stays bf16
       }
+      if (fp8b) { g.w = bw.ff2_w8; g.ab_fp8 = 1; g.acc_scale = bw.ff2_s8; }
       g.variant = t_ff2.variant; g.tile_n = t_ff2.tile_n;
       if (int e = f5_gemm_bf16(&g, st)) return e;
     }

@@ -149,7 +149,8 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   CUtensorMap to, to2;
   {
     const uint64_t orows = batched ? (uint64_t)rpb : (uint64_t)a->m, obat = batched ? (uint64_t)nb : 1;
-    if (int e = make_tmap_out(&to, a->out, a->out_bf16 ? 2 : 4, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo)) return e;
+    F5_REQUIRE(!a->out_fp8 || (a->out_bf16 && a->ldo % 16 == 0), "f5_gemm_bf16: out_fp8 needs out_bf16 = 1 and ldo %% 16 == 0");
+    if (int e = make_tmap_out(&to, a->out, a->out_fp8 ? 1 : (a->out_bf16 ? 2 : 4), (uint64_t)a->n, orows, obat, (uint64_t)a->ldo)) return e;
     if (a->out2_bf16) {
       F5_REQUIRE(!a->out_bf16, "f5_gemm_bf16: out2_bf16 needs an fp32 out");
       if (int e = make_tmap_out(&to2, a->out2_bf16, a->out2_fp8 ? 1 : 2, (uint64_t)a->n, orows, obat, (uint64_t)a->ldo2)) return e;
@@ -211,7 +212,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
     p2.ln_scale = a->ln_scale; p2.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
     p2.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p2.ln_in_units = a->k / 64;
     p2.ln_tab = a->ln_tab; p2.ln_tab_ld = a->ln_tab_ld;
-    p2.ab8 = ab8 ? 1 : 0; p2.acc_scale = ab8 ? a->acc_scale : 1.f; p2.out2_fp8 = a->out2_fp8;
+    p2.ab8 = ab8 ? 1 : 0; p2.acc_scale = ab8 ? a->acc_scale : 1.f; p2.out2_fp8 = a->out2_fp8; p2.out_fp8 = a->out_fp8;
     if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
     CUtensorMap ta2, tb2;
     {
@@ -274,7 +275,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   p.ln_scale = a->ln_scale; p.ln_stats = reinterpret_cast<float2*>(a->ln_stats);
   p.ln_in_stats = reinterpret_cast<const float2*>(a->ln_in_stats); p.ln_in_units = a->k / 64;
   p.ln_tab = a->ln_tab; p.ln_tab_ld = a->ln_tab_ld;
-  p.ab8 = ab8 ? 1 : 0; p.acc_scale = ab8 ? a->acc_scale : 1.f; p.out2_fp8 = a->out2_fp8;
+  p.ab8 = ab8 ? 1 : 0; p.acc_scale = ab8 ? a->acc_scale : 1.f; p.out2_fp8 = a->out2_fp8; p.out_fp8 = a->out_fp8;
   if (a->out2_bf16) F5_REQUIRE(a->ldo2 % 8 == 0 && a->n % 8 == 0, "f5_gemm_bf16: out2 alignment");
 
   // A: (channels, frames, utterances); flat mode is one "utterance" of m rows

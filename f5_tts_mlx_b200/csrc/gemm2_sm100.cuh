@@ -357,6 +357,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.buf2 = LNO ? smem + S::kStage2Offset + grp * 8192 : nullptr;
       stg.buf2_par = 0;
       stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
+      stg.out_fp8 = p.out_fp8;
       stg.map_out = &tma_out;
       stg.map_out2 = &tma_out2;
       if (pair_tiles_per_batch > 0) {

@@ -57,6 +57,7 @@ struct GemmParams {
   int ab8;                 // A and W are e4m3 bytes: 128-element k-blocks, kind::f8f6f4 MMAs
   float acc_scale;         // multiplies the accumulator (the weight tensor's quantisation scale); 1 otherwise
   int out2_fp8;            // the second output is e4m3 (1 byte per element) instead of bf16
+  int out_fp8;             // the primary output is e4m3 (bf16-output instantiations only): 32-byte rows per chunk
 };
 
 // Each CTA touches its 1/num_ctas slice of [pf_ptr, pf_ptr + pf_bytes) with L2 prefetches (one warp,
@@ -209,6 +210,7 @@ struct EpiStage {
   const CUtensorMap* map_out2;
   int c1, c2;              // tensor-map coordinates of tile row 0: row inside the utterance, utterance
   int par_base;            // staging buffer of a chunk = par_base ^ HALF (set by the drain loops)
+  int out_fp8;             // primary output as e4m3 (GemmParams::out_fp8)
   float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics ((0, 1) otherwise)
 };
 
@@ -231,7 +233,17 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
     asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
   }
 #endif
-  if (OUT_BF16) {
+  if (OUT_BF16 && st.out_fp8) {
+    uint8_t* mine = buf + st.r * 32;           // e4m3: 32-byte rows, SWIZZLE_32B
+    const int sw = (st.r >> 2) & 1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<uint4*>(mine + ((j ^ sw) * 16)) =
+          make_uint4(pack_e4m3x4(v[16 * j], v[16 * j + 1], v[16 * j + 2], v[16 * j + 3]),
+                     pack_e4m3x4(v[16 * j + 4], v[16 * j + 5], v[16 * j + 6], v[16 * j + 7]),
+                     pack_e4m3x4(v[16 * j + 8], v[16 * j + 9], v[16 * j + 10], v[16 * j + 11]),
+                     pack_e4m3x4(v[16 * j + 12], v[16 * j + 13], v[16 * j + 14], v[16 * j + 15]));
+  } else if (OUT_BF16) {
     uint8_t* mine = buf + st.r * 64;
     const int sw = (st.r >> 1) & 3;
 #pragma unroll

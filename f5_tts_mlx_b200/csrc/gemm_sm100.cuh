@@ -246,6 +246,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.buf2 = smem + 65536 + grp * 16384;
       stg.buf2_par = 8192;
       stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
+      stg.out_fp8 = p.out_fp8;
       const uint32_t tacc = tmem_base + grp * BNG + ((uint32_t)(lg * 32) << 16);
       if constexpr (kPreloadAll) {
         epi_drain_tile_preloaded<BNG, ACT, OUT_BF16, ROPE>(tacc, bias_s, gate_s, aux_s, cs, res_all, p, n0g, row, b_idx,

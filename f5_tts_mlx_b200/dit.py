@@ -27,7 +27,7 @@ class DitBuffersC(C.Structure):
         ("y_bf16", C.c_void_p), ("x", C.c_void_p), ("h", C.c_void_p), ("a_bf16", C.c_void_p),
         ("c_bf16", C.c_void_p), ("qkv_bf16", C.c_void_p), ("ff_bf16", C.c_void_p), ("v", C.c_void_p),
         ("ln_stats", C.c_void_p), ("ln_tab", C.c_void_p), ("ln_prep", C.c_void_p),
-        ("valid_len", C.c_void_p),
+        ("valid_len", C.c_void_p), ("a_fp8", C.c_void_p),
     ]
 
 
@@ -46,7 +46,7 @@ class DitSession:
     evaluation times, with or without the CFG batch doubling."""
 
     def __init__(self, cfg: DiTConfig, ct_ld: int, batch: int, frames: int, n_times: int, use_cfg: bool,
-                 text_cols: int, device: torch.device, masked: bool, fused_adaln: bool = True):
+                 text_cols: int, device: torch.device, masked: bool, fused_adaln: bool = True, fp8: bool = False):
         self.cfg, self.batch, self.frames, self.n_times, self.use_cfg = cfg, batch, frames, n_times, use_cfg
         self.device = device
         D, F, Ct = cfg.dim, cfg.ff_inner, cfg.text_dim
@@ -87,6 +87,7 @@ class DitSession:
         self.ln_stats = z(R, D // 64, 2) if fused_adaln else None
         self.ln_tab = z(4 * n_times, self.ln_tab_ld) if fused_adaln else None
         self.ln_prep = z(2 * cfg.depth + 1, 4 * n_times, D, dt=bf16) if fused_adaln else None
+        self.a_fp8 = z(R, D, dt=torch.uint8) if (fp8 and fused_adaln) else None   # e4m3 operand of the QKV / FF1 GEMMs
         c = DitBuffersC()
         c.batch, c.frames, c.cfg, c.n_times = batch, frames, int(use_cfg), n_times
         c.text_len_max, c.drop_flags = self.text.shape[1], 0
@@ -140,7 +141,7 @@ class DiT:
 
     def __init__(self, *, dim, depth=8, heads=8, dim_head=64, dropout=0.0, ff_mult=4, mel_dim=100,
                  text_num_embeds=256, text_dim=None, text_mask_padding=True, conv_layers=0,
-                 device: str | torch.device = "cuda", fused_adaln: bool = True):
+                 device: str | torch.device = "cuda", fused_adaln: bool = True, fp8: bool = False):
         if text_dim is None:
             text_dim = mel_dim
         if dim_head != 64 or dim != heads * dim_head:
@@ -158,6 +159,13 @@ class DiT:
         # AdaLN LayerNorm+modulate folded into the neighbouring GEMM epilogues (default); False keeps the separate
         # f5_ln_modulate launches (the r01 path — kept for A/B measurements and as a cross-check in the tests)
         self.fused_adaln = bool(fused_adaln)
+        # FP8 mode — the B200 analogue of the reference's quantised `--q` checkpoints (cfm.py:451-452,510-515): the
+        # QKV and FF1 GEMMs (63 % of a block's FLOPs) run on e4m3 operands (kind::f8f6f4 MMAs): weights quantised per
+        # tensor at pack time, activations written as e4m3 by the producing GEMM's epilogue.  Lossy like `--q`; gated
+        # by the same derived-drift rule against the oracle's e4m3 emulation (tests/test_gpu_parity.py).
+        self.fp8 = bool(fp8)
+        if self.fp8 and not self.fused_adaln:
+            raise ValueError("fp8=True needs fused_adaln=True (the e4m3 operand is written by the GEMM epilogues)")
         self.device = torch.device(device)
         self.packed: Optional[PackedDiT] = None
         self._sessions: Dict[tuple, DitSession] = {}
@@ -170,12 +178,12 @@ class DiT:
         W = dict(weights)
         if not any(k.startswith("transformer.") for k in W):
             W = {"transformer." + k: v for k, v in W.items()}
-        self.packed = PackedDiT(self.config, self.device).load(W)
+        self.packed = PackedDiT(self.config, self.device, fp8=self.fp8).load(W)
         return self
 
     def allocate_weights(self) -> "DiT":
         """Allocate the packed buffer without filling it (non-source ranks before the broadcast)."""
-        self.packed = PackedDiT(self.config, self.device)
+        self.packed = PackedDiT(self.config, self.device, fp8=self.fp8)
         return self
 
     def _require_weights(self) -> PackedDiT:
@@ -186,13 +194,13 @@ class DiT:
     # -- sessions --
     def session(self, batch: int, frames: int, n_times: int, use_cfg: bool, text_cols: int,
                 masked: bool, bucketed: bool = False) -> DitSession:
-        key = (batch, frames, n_times, use_cfg, text_cols, masked, self.fused_adaln, bucketed)
+        key = (batch, frames, n_times, use_cfg, text_cols, masked, self.fused_adaln, bucketed, self.fp8)
         s = self._sessions.pop(key, None)
         if s is None:
             while len(self._sessions) >= self.session_cache_size:
                 self._sessions.pop(next(iter(self._sessions)))
             s = DitSession(self.config, self._require_weights().ct_ld, batch, frames, n_times, use_cfg,
-                           text_cols, self.device, masked, self.fused_adaln)
+                           text_cols, self.device, masked, self.fused_adaln, self.fp8)
             if bucketed:
                 s.use_bucketing()
         self._sessions[key] = s          # LRU order: most recently used last

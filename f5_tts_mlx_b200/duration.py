@@ -124,7 +124,7 @@ class DurationPredictor:
                 setattr(tbs[i], n, T[f"tb{i}.{n}"].data_ptr())
         blks = (DitBlockWeightsC * tr.depth)()
         for i in range(tr.depth):
-            for n, _ in DitBlockWeightsC._fields_:
+            for n, _ in DitBlockWeightsC._fields_[:8]:          # the FP8 fields stay NULL: the duration model runs in bf16
                 setattr(blks[i], n, T[f"blk{i}.{n}"].data_ptr())
         c.text_blocks, c.blocks = tbs, blks
         for j in range(2):

@@ -60,9 +60,17 @@ def gemm(
     ln_stats: torch.Tensor | None = None,      # f32 [rows, n/64, 2] (sum, sum of squares) per 64 columns
     ln_in_stats: torch.Tensor | None = None,   # f32 [rows, k/64, 2]: consumer mode
     ln_tab: torch.Tensor | None = None,        # f32 [4, >=n] rows c1_hi, c1_lo, c2_hi, c2_lo
+    ab_fp8: bool = False,                      # a and w are e4m3 bytes (uint8 / float8_e4m3fn tensors), k % 128 == 0
+    acc_scale: float = 1.0,                    # multiplies the accumulator in FP8 mode (weight tensor scale)
+    out2_fp8: bool = False,                    # out2 is written as e4m3 bytes (uint8 tensor)
+    out_fp8: bool = False,                     # out (a uint8 tensor) is written as e4m3 bytes
 ) -> torch.Tensor:
     _need_cuda(a, w, out, bias, resid, gate, row_len, rope, out2, ln_scale, ln_stats, ln_in_stats, ln_tab)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    if ab_fp8:
+        a = a.view(torch.uint8) if a.dtype != torch.uint8 else a
+        w = w.view(torch.uint8) if w.dtype != torch.uint8 else w
+    else:
+        assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
     m = a.shape[0]
     g = _lib.GemmArgs()
@@ -76,8 +84,9 @@ def gemm(
     g.batched_tiles = int(batched_tiles)
     g.conv_taps, g.conv_pad, g.conv_grouped = conv_taps, conv_pad, int(conv_grouped)
     g.act = act
-    g.out_bf16 = int(out.dtype == torch.bfloat16)
-    assert out.dtype in (torch.bfloat16, torch.float32)
+    g.out_bf16 = int(out.dtype == torch.bfloat16 or out_fp8)
+    g.out_fp8 = int(out_fp8)
+    assert out.dtype in (torch.bfloat16, torch.float32) or (out_fp8 and out.dtype == torch.uint8)
     g.bias = bias.data_ptr() if bias is not None else None
     g.out, g.ldo = out.data_ptr(), out.stride(0)
     if resid is not None:
@@ -97,8 +106,9 @@ def gemm(
     g.variant = variant
     if debug_ts is not None:
         g.debug_ts = debug_ts.data_ptr()
+    g.ab_fp8, g.acc_scale, g.out2_fp8 = int(ab_fp8), float(acc_scale), int(out2_fp8)
     if out2 is not None:
-        assert out2.dtype == torch.bfloat16 and out2.stride(-1) == 1
+        assert out2.dtype == (torch.uint8 if out2_fp8 else torch.bfloat16) and out2.stride(-1) == 1
         g.out2_bf16, g.ldo2 = out2.data_ptr(), out2.stride(0)
     if ln_scale is not None:
         assert ln_scale.dtype == torch.float32 and ln_stats is not None and ln_stats.dtype == torch.float32

@@ -274,7 +274,23 @@ class ConvNextWeightsC(C.Structure):
 
 class DitBlockWeightsC(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("qkv_w", "qkv_b", "out_w", "out_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b")]
+                ("qkv_w", "qkv_b", "out_w", "out_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b", "qkv_w8", "ff1_w8", "out_w8",
+                 "ff2_w8")] + \
+               [("qkv_s8", C.c_float), ("ff1_s8", C.c_float), ("out_s8", C.c_float), ("ff2_s8", C.c_float)]
+
+
+E4M3_MAX = 448.0
+
+
+def quantize_e4m3(w: torch.Tensor):
+    """Per-tensor e4m3 quantisation of a weight matrix: w ~= scale * q, q in float8_e4m3fn (round to nearest even,
+    |q| <= 448).  Returns (bytes as uint8 tensor, scale)."""
+    w = w.detach().float()
+    scale = float(w.abs().max().item()) / E4M3_MAX
+    if scale == 0.0:
+        scale = 1.0
+    q = (w / scale).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8), scale
 
 
 class DitWeightsC(C.Structure):
@@ -333,14 +349,15 @@ class PackedDiT:
 
     ALIGN = 256
 
-    def __init__(self, cfg: DiTConfig, device: torch.device | str = "cuda"):
+    def __init__(self, cfg: DiTConfig, device: torch.device | str = "cuda", fp8: bool = False):
         self.cfg = cfg
         self.device = torch.device(device)
+        self.fp8 = bool(fp8)           # also keep e4m3 copies of the QKV / FF1 weights (appended after the bf16 layout)
         self.ct_ld = _round_up(cfg.mel_dim + cfg.text_dim, 64)
         self.specs: Dict[str, _Spec] = {}
         off = 0
         for name, shape, dtype in self._layout():
-            nbytes = int(np.prod(shape)) * (2 if dtype == torch.bfloat16 else 4)
+            nbytes = int(np.prod(shape)) * self._esize(dtype)
             self.specs[name] = _Spec(name, tuple(shape), dtype, off)
             off = _round_up(off + nbytes, self.ALIGN)
         self.nbytes = off
@@ -389,11 +406,22 @@ class PackedDiT:
             yield f"blk{i}.ff2_b", (D,), f32
         yield "proj_w", (c.mel_dim, D), bf
         yield "proj_b", (c.mel_dim,), f32
+        if self.fp8:       # FP8 mode: appended, so the bf16 prefix is the layout the C packer (f5_pack_weights) knows
+            for i in range(c.depth):
+                yield f"blk{i}.qkv_w8", (3 * D, D), torch.uint8
+                yield f"blk{i}.ff1_w8", (F, D), torch.uint8
+                yield f"blk{i}.out_w8", (D, D), torch.uint8
+                yield f"blk{i}.ff2_w8", (D, F), torch.uint8
+            yield "fp8_scales", (c.depth, 4), f32       # (qkv, ff1, out, ff2) per block: travels with the ONE broadcast
+
+    @staticmethod
+    def _esize(dtype) -> int:
+        return {torch.bfloat16: 2, torch.uint8: 1}.get(dtype, 4)
 
     def view(self, name: str) -> torch.Tensor:
         s = self.specs[name]
         n = int(np.prod(s.shape))
-        nbytes = n * (2 if s.dtype == torch.bfloat16 else 4)
+        nbytes = n * self._esize(s.dtype)
         return self.buffer[s.offset:s.offset + nbytes].view(s.dtype).view(s.shape)
 
     def _put(self, name: str, t: torch.Tensor) -> None:
@@ -449,6 +477,14 @@ class PackedDiT:
             self._put(f"blk{i}.ff1_b", g(p + "ff.ff.layers.0.layers.0.bias"))
             self._put(f"blk{i}.ff2_w", g(p + "ff.ff.layers.2.weight"))
             self._put(f"blk{i}.ff2_b", g(p + "ff.ff.layers.2.bias"))
+            if self.fp8:
+                for j, (dst, wt) in enumerate(((f"blk{i}.qkv_w8", torch.cat([g(p + f"attn.to_{n}.weight") for n in "qkv"], 0)),
+                                               (f"blk{i}.ff1_w8", g(p + "ff.ff.layers.0.layers.0.weight")),
+                                               (f"blk{i}.out_w8", g(p + "attn.to_out.layers.0.weight")),
+                                               (f"blk{i}.ff2_w8", g(p + "ff.ff.layers.2.weight")))):
+                    q, sc = quantize_e4m3(wt)
+                    self.view(dst).copy_(q)
+                    self.view("fp8_scales")[i, j] = sc
         self._put("proj_w", g(T + "proj_out.weight"))
         self._put("proj_b", g(T + "proj_out.bias"))
         return self
@@ -479,8 +515,14 @@ class PackedDiT:
                 setattr(tbs[i], n, ptr(f"tb{i}.{n}"))
         blks = (DitBlockWeightsC * c.depth)()
         for i in range(c.depth):
-            for n, _ in DitBlockWeightsC._fields_:
+            for n, _ in DitBlockWeightsC._fields_[:8]:
                 setattr(blks[i], n, ptr(f"blk{i}.{n}"))
+            if self.fp8:
+                sc = self.view("fp8_scales").cpu()
+                blks[i].qkv_w8, blks[i].ff1_w8 = ptr(f"blk{i}.qkv_w8"), ptr(f"blk{i}.ff1_w8")
+                blks[i].out_w8, blks[i].ff2_w8 = ptr(f"blk{i}.out_w8"), ptr(f"blk{i}.ff2_w8")
+                blks[i].qkv_s8, blks[i].ff1_s8 = float(sc[i, 0]), float(sc[i, 1])
+                blks[i].out_s8, blks[i].ff2_s8 = float(sc[i, 2]), float(sc[i, 3])
         w.text_blocks = tbs
         w.blocks = blks
         for j in range(2):

@@ -131,7 +131,7 @@ typedef struct f5_gemm_args {
   int32_t ab_fp8;
   int32_t out2_fp8;
   float acc_scale;
-  int32_t reserved_fp8;
+  int32_t out_fp8;        /* with out_bf16 = 1: `out` is written as e4m3 bytes instead (ldo in bytes, multiple of 16) */
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
@@ -149,6 +149,10 @@ int f5_debug_gemm_ts(void* base, int64_t stride_bytes, int32_t max_calls);
 int f5_attention_fwd(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch,
                      int32_t frames, int32_t heads, int32_t head_dim, const int32_t* kv_len,
                      void* stream);
+/* the same with an e4m3 output (ld_out in bytes): the A operand of the FP8-mode out-projection */
+int f5_attention_fwd_e4m3(const void* qkv, int64_t ld_qkv, void* out, int64_t ld_out, int32_t batch,
+                          int32_t frames, int32_t heads, int32_t head_dim, const int32_t* kv_len,
+                          void* stream);
 /* debug aid: while `base` is non-NULL, attention launches write SM-clock stamps of CTA (0,0,0) into it:
    uint64 [3 roles (softmax group 0, group 1, MMA warp)][64 key tiles][8 slots]; NULL switches it off. */
 int f5_debug_attention_ts(void* base);
@@ -202,6 +206,11 @@ typedef struct f5_dit_block_weights {
   const void* out_w;  const float* out_b;   /* [D, D]                     (dit.py:124)     */
   const void* ff1_w;  const float* ff1_b;   /* [F, D]                     (dit.py:94-95)   */
   const void* ff2_w;  const float* ff2_b;   /* [D, F]                     (dit.py:96)      */
+  /* FP8 mode (optional, NULL = bf16 only): e4m3 copies of the QKV / FF1 weights, ONE scale per tensor
+   * (w ~= scale * e4m3); used by f5_dit_forward when f5_dit_buffers.a_fp8 is set (see f5_gemm_args.ab_fp8).  With
+   * out_w8 / ff2_w8 also the out-projection (attention writes e4m3) and FF2 (FF1 writes e4m3) run in FP8. */
+  const void* qkv_w8; const void* ff1_w8; const void* out_w8; const void* ff2_w8;
+  float qkv_s8, ff1_s8, out_s8, ff2_s8;
 } f5_dit_block_weights;
 
 typedef struct f5_dit_weights {
@@ -268,6 +277,9 @@ typedef struct f5_dit_buffers {
    * zero where the reference's zero padding would be seen (the k=31 ConvPositionEmbedding input, dit.py:45) and are
    * masked as attention keys, so rows < N equal the unpadded computation.  NULL = all `frames` rows are real. */
   const int32_t* valid_len;   /* int32 [rows/frames], every entry the same N <= frames, or NULL */
+  /* FP8 mode: e4m3 [rows, D] — the AdaLN-modulated operand of the QKV / FF1 GEMMs (written by the producing GEMM's
+   * epilogue instead of a_bf16); requires the fused AdaLN buffers and blocks[i].qkv_w8 / ff1_w8.  NULL = bf16. */
+  void* a_fp8;
 } f5_dit_buffers;
 
 /* step-invariant work, once per sample(): text embedding (dit.py:196-229), hoisted conditioning

@@ -45,10 +45,17 @@ Weights = Dict[str, Tensor]
 class Precision:
     """fp32 everywhere (the reference), or bf16-rounded tensor-core operands (the CUDA path)."""
 
-    def __init__(self, emulate_bf16: bool = False, ln_by_linearity: bool = False):
+    def __init__(self, emulate_bf16: bool = False, ln_by_linearity: bool = False, fp8: bool = False):
         self.emulate_bf16 = emulate_bf16
         # rounding points of the CUDA path's fused AdaLN (see adaln_linear below); only meaningful with emulate_bf16
         self.ln_by_linearity = ln_by_linearity
+        # FP8 mode of the CUDA path (DiT(fp8=True)): the four GEMMs of every DiT block multiply e4m3 operands — weights
+        # quantised per tensor (scale = max|w| / 448), activations rounded to e4m3 by the producing kernel (no scale)
+        self.fp8 = fp8
+
+    @staticmethod
+    def e4m3(x: Tensor) -> Tensor:
+        return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
 
     def op(self, x: Tensor) -> Tensor:
         return x.bfloat16().float() if self.emulate_bf16 else x
@@ -63,7 +70,7 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor], prec: Precision = FP32) ->
 
 
 def adaln_linear(x: Tensor, scale: Tensor, shift: Tensor, w: Tensor, b: Optional[Tensor], prec: Precision = FP32,
-                 eps: float = 1e-6) -> Tensor:
+                 eps: float = 1e-6, fp8_scale: Optional[float] = None) -> Tensor:
     """Linear(LayerNorm(x) * (1 + scale) + shift) — dit.py:270 + the Linear that consumes it (dit.py:136-143, 94,
     398).  fp32: exactly that.  With `prec.ln_by_linearity` it applies the CUDA path's rounding points: the
     producer GEMM's epilogue stores bf16(x * (1 + scale)) and per-row (mean, M2); the consumer GEMM multiplies that
@@ -77,8 +84,12 @@ def adaln_linear(x: Tensor, scale: Tensor, shift: Tensor, w: Tensor, b: Optional
     rstd = torch.rsqrt(x.var(dim=-1, unbiased=False, keepdim=True) + eps)
     wb = prec.op(w)
     xt = prec.op(x * (1 + scale[:, None]))
-    c1 = F.linear(1 + scale, wb)[:, None]
+    c1 = F.linear(1 + scale, wb)[:, None]          # the tables always come from the bf16 weights
     c2 = F.linear(shift, wb, b)[:, None]
+    if prec.fp8 and fp8_scale is not None:
+        # FP8 mode: e4m3 activation (unscaled) x e4m3 weight (per-tensor scale), fp32 accumulation
+        acc = F.linear(Precision.e4m3(x * (1 + scale[:, None])), Precision.e4m3(w / fp8_scale)) * fp8_scale
+        return rstd * (acc - mu * c1) + c2
     return rstd * (F.linear(xt, wb) - mu * c1) + c2
 
 
@@ -329,7 +340,10 @@ def attention(x: Tensor, mask: Optional[Tensor], rope: Tensor, W: Weights, pfx: 
     dit.py:161-166 (the reference's `.expand` call is not an mx.array method)."""
     b, n, _ = x.shape
     if adaln is not None:   # x is the un-normalised stream; AdaLayerNormZero (dit.py:270) feeds to_q/k/v (dit.py:313-316)
-        lin = lambda w, bb: adaln_linear(x, adaln[0], adaln[1], w, bb, prec)
+        s8 = None
+        if prec.fp8:        # ONE scale for the fused [3D, D] weight, as the CUDA pack quantises it
+            s8 = max(float(W[pfx + f"to_{n}.weight"].abs().max()) for n in "qkv") / 448.0
+        lin = lambda w, bb: adaln_linear(x, adaln[0], adaln[1], w, bb, prec, fp8_scale=s8)
     else:
         lin = lambda w, bb: linear(x, w, bb, prec)
     q = lin(W[pfx + "to_q.weight"], W[pfx + "to_q.bias"])
@@ -354,7 +368,12 @@ def attention(x: Tensor, mask: Optional[Tensor], rope: Tensor, W: Weights, pfx: 
     else:
         o = torch.matmul(p, v)
     o = o.permute(0, 2, 1, 3).reshape(b, n, -1)
-    o = linear(prec.op(o), W[pfx + "to_out.layers.0.weight"], W[pfx + "to_out.layers.0.bias"], prec)
+    if prec.fp8:   # FP8 mode: the attention output leaves the kernel as e4m3, the out-projection weight is e4m3 (per tensor)
+        wo = W[pfx + "to_out.layers.0.weight"]
+        so = float(wo.abs().max()) / 448.0
+        o = F.linear(Precision.e4m3(o), Precision.e4m3(wo / so)) * so + W[pfx + "to_out.layers.0.bias"]
+    else:
+        o = linear(prec.op(o), W[pfx + "to_out.layers.0.weight"], W[pfx + "to_out.layers.0.bias"], prec)
     if mask is not None:
         o = o * mask[:, :, None]                                          # :172-173
     return o
@@ -369,10 +388,16 @@ def dit_block(x: Tensor, t: Tensor, mask: Optional[Tensor], rope: Tensor, W: Wei
     shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
     attn_out = attention(x, mask, rope, W, p + "attn.", cfg.heads, prec, adaln=(scale_msa, shift_msa))
     x = x + gate_msa[:, None] * attn_out
-    h = adaln_linear(x, scale_mlp, shift_mlp, W[p + "ff.ff.layers.0.layers.0.weight"],
-                     W[p + "ff.ff.layers.0.layers.0.bias"], prec)
+    w1 = W[p + "ff.ff.layers.0.layers.0.weight"]
+    h = adaln_linear(x, scale_mlp, shift_mlp, w1, W[p + "ff.ff.layers.0.layers.0.bias"], prec,
+                     fp8_scale=(float(w1.abs().max()) / 448.0) if prec.fp8 else None)
     h = F.gelu(h, approximate="tanh")
-    ff = linear(h, W[p + "ff.ff.layers.2.weight"], W[p + "ff.ff.layers.2.bias"], prec)
+    if prec.fp8:   # FF1's epilogue writes e4m3, FF2's weight is e4m3 (per tensor)
+        w2 = W[p + "ff.ff.layers.2.weight"]
+        s2 = float(w2.abs().max()) / 448.0
+        ff = F.linear(Precision.e4m3(h), Precision.e4m3(w2 / s2)) * s2 + W[p + "ff.ff.layers.2.bias"]
+    else:
+        ff = linear(h, W[p + "ff.ff.layers.2.weight"], W[p + "ff.ff.layers.2.bias"], prec)
     return x + gate_mlp[:, None] * ff
 
 

@@ -7,8 +7,9 @@ dev = "cuda"; lib = _lib.load()
 cfg = BASE_CONFIG
 fused = os.environ.get("F5_FUSED", "1") != "0"
 B = int(os.environ.get("F5_B", "1"))
+fp8 = os.environ.get("F5_FP8", "0") == "1"
 model = DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, text_num_embeds=cfg.text_num_embeds,
-            text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev, fused_adaln=fused).load_weights(random_dit_weights(cfg))
+            text_dim=cfg.text_dim, conv_layers=cfg.conv_layers, device=dev, fused_adaln=fused, fp8=fp8).load_weights(random_dit_weights(cfg))
 g = torch.Generator().manual_seed(3)
 N, nref = 937, 328
 cond = (torch.randn(B, nref, 100, generator=g) * 2.24 - 1.27).to(dev)
@@ -29,7 +30,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 plan.y.copy_(y0); e0.record(); plan.graph.replay(); e1.record(); torch.cuda.synchronize()
-print(f"fused={fused} B={B} graph replay (3 intervals): {e0.elapsed_time(e1):.3f} ms")
+print(f"fp8={fp8} fused={fused} B={B} graph replay (3 intervals): {e0.elapsed_time(e1):.3f} ms")
 t = ts.cpu().numpy().reshape(NCALL, NCTA, 10).astype(np.float64)
 used = [i for i in range(NCALL) if t[i, :, 0].max() > 0]
 pre = 2 * 4 + 1 + 1 + (2 * cfg.depth + 1 if fused else 0)      # precompute GEMMs (text blocks, hoist, mod table, LN tables)

@@ -224,3 +224,81 @@ def test_gemm_fused_ln_consumer(M, D, N, act, rope):
         ref = r2.reshape(M, N).clone(); ref[:, : N // 3] *= 0.125
     # the operand is bf16(x (1+s)): its rounding error is relative to |x| (not |x - mean|); mean/std here is 0.24
     assert rel(out, ref) < 6e-3
+
+
+# ---------------- FP8 mode (e4m3 operands, kind::f8f6f4) ----------------
+def _e4m3(x):
+    return x.clamp(-448, 448).to(torch.float8_e4m3fn)
+
+
+@pytest.mark.parametrize("M,N,K,variant,tile,act", [(1874, 3072, 1024, 0, 0, 0), (1874, 2048, 1024, 0, 0, 1), (300, 256, 128, 1, 0, 0),
+                                                     (257, 512, 256, 1, 64, 0), (700, 1024, 1024, 2, 256, 0), (40000, 2048, 1024, 0, 0, 1)])
+def test_gemm_fp8_operands(M, N, K, variant, tile, act):
+    """f5_gemm_args.ab_fp8: A and W as e4m3 bytes, fp32 accumulation, accumulator x acc_scale + bias (+ GELU), bf16 out —
+    against the fp32 product of the SAME e4m3 values (exact products, so only the summation order differs)."""
+    from f5_tts_mlx_b200 import ops
+    a8 = _e4m3(rnd(M, K) * 1.5); wf = rnd(N, K, scale=K ** -0.5); bias = rnd(N)
+    sc = float(wf.abs().max()) / 448.0
+    w8 = _e4m3(wf / sc)
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    ops.gemm(a8, w8, out, bias=bias, act=act, ab_fp8=True, acc_scale=sc, variant=variant, tile_n=tile)
+    ref = (a8.float() @ w8.float().T) * sc + bias
+    if act == 1:
+        ref = F.gelu(ref, approximate="tanh")
+    assert rel(out, ref) < 4e-3
+
+
+def test_gemm_fp8_second_output_and_consumer_chain():
+    """Producer writes the fused-LN operand as e4m3 (out2_fp8), an FP8-mode consumer multiplies it: the chain the
+    DiT block runs in FP8 mode, against fp32 torch on the same quantised values."""
+    from f5_tts_mlx_b200 import ops
+    M, D, K, N = 1874, 1024, 1024, 2048
+    a = rnd(M, K).bfloat16(); w = rnd(D, K, scale=K ** -0.5).bfloat16(); bias = rnd(D)
+    gate = rnd(1, D); x = rnd(M, D) * 2 + 0.3; x0 = x.clone(); s = rnd(D, seed=5) * 0.3
+    xt8 = torch.zeros(M, D, device=dev, dtype=torch.uint8)
+    stats = torch.zeros(M, D // 64, 2, device=dev)
+    ops.gemm(a, w, x, bias=bias, resid=x, gate=gate[0], out2=xt8, ln_scale=s, ln_stats=stats, out2_fp8=True)
+    xref = x0 + gate * (a.float() @ w.float().T + bias)
+    want = _e4m3(xref * (1 + s))
+    got = xt8.view(torch.float8_e4m3fn)
+    assert (got.float() == want.float()).float().mean().item() > 0.995          # ties / 1-ulp fp32 differences only
+    assert rel(got.float(), want.float()) < 5e-3
+    # consumer in FP8 mode on that operand
+    b2 = rnd(D, seed=8) * 0.5
+    w2f = rnd(N, D, scale=D ** -0.5); bias2 = rnd(N); sc = float(w2f.abs().max()) / 448.0
+    w28 = _e4m3(w2f / sc)
+    tab = _ln_tab(s, b2, w2f.bfloat16())
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(xt8, w28, out, bias=bias2, act=1, ln_in_stats=stats, ln_tab=tab, ab_fp8=True, acc_scale=sc)
+    mu = xref.mean(-1, keepdim=True); rstd = torch.rsqrt(xref.var(-1, unbiased=False, keepdim=True) + 1e-6)
+    acc = (got.float() @ w28.float().T) * sc
+    c1 = (1 + s) @ w2f.bfloat16().float().T; c2 = b2 @ w2f.bfloat16().float().T + bias2
+    ref = F.gelu(rstd * (acc - mu * c1) + c2, approximate="tanh")
+    assert rel(out, ref) < 6e-3
+
+
+def test_gemm_fp8_primary_output_and_attention_e4m3_output():
+    """FF1 in FP8 mode writes its GELU output as e4m3 (the A operand of FF2); the attention kernel writes e4m3 for the
+    out-projection: both against the e4m3 rounding of the fp32 reference."""
+    from f5_tts_mlx_b200 import _lib, ops
+    M, K, N = 1874, 1024, 2048
+    a8 = _e4m3(rnd(M, K) * 1.5); wf = rnd(N, K, scale=K ** -0.5); bias = rnd(N)
+    sc = float(wf.abs().max()) / 448.0
+    w8 = _e4m3(wf / sc)
+    out8 = torch.zeros(M, N, device=dev, dtype=torch.uint8)
+    ops.gemm(a8, w8, out8, bias=bias, act=1, ab_fp8=True, acc_scale=sc, out_fp8=True)
+    ref = F.gelu((a8.float() @ w8.float().T) * sc + bias, approximate="tanh")
+    got = out8.view(torch.float8_e4m3fn).float()
+    assert (got == _e4m3(ref).float()).float().mean().item() > 0.99
+    assert rel(got, ref) < 4e-2                                   # e4m3 rounding of the output itself (2^-4 relative)
+    # attention with e4m3 output
+    B, NF, H = 2, 937, 16
+    D = H * 64
+    qkv = (rnd(B * NF, 3 * D) * 0.5).bfloat16()
+    o16 = torch.empty(B * NF, D, device=dev, dtype=torch.bfloat16)
+    o8 = torch.zeros(B * NF, D, device=dev, dtype=torch.uint8)
+    lib = _lib.load(); st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.f5_attention_fwd(qkv.data_ptr(), 3 * D, o16.data_ptr(), D, B, NF, H, 64, None, st))
+    _lib.check(lib.f5_attention_fwd_e4m3(qkv.data_ptr(), 3 * D, o8.data_ptr(), D, B, NF, H, 64, None, st))
+    g8 = o8.view(torch.float8_e4m3fn).float()
+    assert rel(g8, o16.float()) < 4e-2 and (g8 - o16.float()).abs().max().item() <= 0.07 * o16.float().abs().max().item() + 2e-3

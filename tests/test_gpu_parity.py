@@ -488,3 +488,40 @@ def test_frame_bucketing_one_plan_for_many_lengths_same_results(gate):
         ref, _ = O.sample(cond.cpu(), text, N, W, ocfg_of(cfg), y0=y0, **kw)
         assert rel(b.cpu(), ref) < 1e-2
     assert len(plans) == 1 and bucketed.last_plan.session.frames == 256
+
+
+def test_fp8_mode_forward_within_derived_drift(base):
+    """DiT(fp8=True): the four GEMMs of every block on e4m3 operands (weights quantised per tensor at pack time,
+    activations written as e4m3 by the producing kernels) — the B200 analogue of the reference's lossy `--q`
+    checkpoints.  Same rule as everywhere: within 3x the drift of the oracle's emulation of exactly these rounding
+    points (Precision(fp8=True)), which is ~7x the bf16 drift."""
+    cfg, W, model = base
+    m8 = make_dit_fp8(cfg, W)
+    g = torch.Generator().manual_seed(2)
+    N = 937
+    x = torch.randn(1, N, 100, generator=g); cond = (torch.randn(1, N, 100, generator=g) * 2.24 - 1.27); cond[:, 328:] = 0
+    text = torch.randint(0, 2545, (1, 152), generator=g, dtype=torch.int32)
+    t = torch.tensor(0.25)
+    ref = O.dit_forward(x, cond, text, t, False, False, None, W, ocfg_of(cfg))
+    ref8 = O.dit_forward(x, cond, text, t, False, False, None, W, ocfg_of(cfg), O.Precision(True, True, True))
+    got = m8(x.to(dev), cond.to(dev), text.to(dev), t).cpu()
+    drift = rel(ref8, ref)
+    r = rel(got, ref)
+    assert 5e-3 < drift < 5e-2 and r < min(3 * drift, 1e-1), (r, drift)
+    assert rel(got, ref8) < 2.0 * drift                     # and close to the emulation itself
+    # through the integrator (8 Euler grid points, CFG): the e4m3 noise does not blow up
+    from f5_tts_mlx_b200 import F5TTS
+    nref = 328
+    kw = dict(steps=8, method="euler", cfg_strength=2.0, sway_sampling_coef=-1.0, y0=x)
+    out, _ = F5TTS(m8).sample(cond[:, :nref].to(dev), text, N, **kw)
+    out16, _ = F5TTS(model).sample(cond[:, :nref].to(dev), text, N, **kw)
+    assert torch.isfinite(out).all() and rel(out[:, nref:], out16[:, nref:]) < 1e-1
+    del m8
+    torch.cuda.empty_cache()
+
+
+def make_dit_fp8(cfg, W):
+    from f5_tts_mlx_b200 import DiT
+    return DiT(dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, ff_mult=cfg.ff_mult, mel_dim=cfg.mel_dim,
+               text_num_embeds=cfg.text_num_embeds, text_dim=cfg.text_dim, conv_layers=cfg.conv_layers,
+               device=dev, fp8=True).load_weights(W)
