@@ -1,7 +1,6 @@
-// Host launcher + C-ABI entry for the tcgen05 flash-attention forward (attention_sm100.cuh).
+// Host launcher + C-ABI entry for the tcgen05 flash-attention forward (attention2_sm100.cuh).
 #include <stdlib.h>
 
-#include "attention_sm100.cuh"
 #include "attention2_sm100.cuh"
 #include "host_common.h"
 
@@ -46,23 +45,17 @@ static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = (int)ld_out;
   p.handoff = 1;
-  // F5_ATTN_VARIANT: 4 (default) two query tiles per CTA, S/P/O in TMEM; 2 same with P in shared memory;
-  // 1 first version.  F5_ATTN_HANDOFF: 2 (default) a softmax group is
-  // released when the other is half way through its exponentials, 1 strict alternation, 0 off.
-  // F5_ATTN_POLY: pairs per 8 exponentials evaluated on the FMA pipe (0 default; 1, 2 measured no faster).
-  static int variant = -1, handoff = 2, poly = 0;
-  if (variant < 0) {
-    const char* v = getenv("F5_ATTN_VARIANT");
+  // F5_ATTN_HANDOFF: 2 (default) a softmax group is released when the other is half way through its exponentials,
+  // 1 strict alternation, 0 off.  (The smem-P variant and the polynomial-exp2 variants of round 1 — measured neutral or
+  // slower — are no longer instantiated; the template parameters document them.)
+  static int handoff = -1;
+  if (handoff < 0) {
     const char* ho = getenv("F5_ATTN_HANDOFF");
-    const char* po = getenv("F5_ATTN_POLY");
-    if (ho && ho[0] >= '0' && ho[0] <= '2') handoff = ho[0] - '0';
-    if (po && po[0] >= '0' && po[0] <= '2') poly = po[0] - '0';
-    variant = (v && (v[0] == '1' || v[0] == '2' || v[0] == '4')) ? v[0] - '0' : 4;
+    handoff = (ho && ho[0] >= '0' && ho[0] <= '2') ? ho[0] - '0' : 2;
   }
   p.handoff = handoff;
   p.ts = g_attn_ts;
   p.out_fp8 = out_fp8;
-  F5_REQUIRE(!out_fp8 || variant == 4, "f5_attention_fwd_e4m3: only the default kernel variant writes e4m3");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   ProfScope ps(PROF_ATTN, 4.0 * batch * heads * (double)frames * frames * 64.0,
                2.0 * batch * (double)frames * heads * 64.0 * 4.0, stream);
@@ -74,10 +67,6 @@ static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld
     return 0;
   };
   const dim3 grid256(cdiv(frames, 256), heads, batch);
-  static SmemAttrOnce o1, o2, o4, o41, o42;
-  if (variant == 2) return launch(attn2_fwd_kernel<false, 0>, o2, grid256, 384, Attn2Smem::kTotal);
-  if (variant == 4 && poly == 1) return launch(attn2_fwd_kernel<true, 1>, o41, grid256, 384, Attn2Smem::kTotal);
-  if (variant == 4 && poly == 2) return launch(attn2_fwd_kernel<true, 2>, o42, grid256, 384, Attn2Smem::kTotal);
-  if (variant == 4) return launch(attn2_fwd_kernel<true, 0>, o4, grid256, 384, Attn2Smem::kTotal);
-  return launch(attn_fwd_kernel, o1, dim3(cdiv(frames, 128), heads, batch), 192, AttnSmem::kTotal);
+  static SmemAttrOnce o4;
+  return launch(attn2_fwd_kernel<true, 0>, o4, grid256, 384, Attn2Smem::kTotal);
 }

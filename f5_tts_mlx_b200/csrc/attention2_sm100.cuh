@@ -1,6 +1,7 @@
 // Flash-attention forward v2 for sm_100a (head_dim 64, non-causal, key-padding mask): two 128-query
 // tiles per CTA ping-pong on one tensor-core stream, accumulator O kept in TMEM with lazy rescaling.
-// Same contract as attention_sm100.cuh (replaces mx.fast.scaled_dot_product_attention, dit.py:166).
+// Non-causal flash-attention forward (replaces mx.fast.scaled_dot_product_attention + the head split / merge,
+// dit.py:141-143,161-167).  The first version (one query tile per CTA, O in registers) is in the history at 0dd48cd.
 //
 //   warp 0      TMA: Q0,Q1 once; K/V 128-key tiles in 2-stage rings
 //   warp 1, 2   MMA issuers, one per query tile g (order per tile:  S_g(0) | S_g(j+1) PV_g(j) | ...)
@@ -23,9 +24,21 @@
 //     starts its exponentials when the other one is half way through its own.
 // B2 N937 H16: 22.1 -> 18.4 us; B128: 1153 -> 990 us (cuDNN SDPA on the same box: 17.3 / 651 us).
 #pragma once
-#include "attention_sm100.cuh"
+#include "ptx.cuh"
 
 namespace f5 {
+
+struct AttnParams {
+  int B, N, H;
+  const int* kv_len;       // [B] valid keys per utterance, or null (= N)
+  __nv_bfloat16* out;      // [B*N, H*64]
+  int ldo;
+  unsigned long long* ts;  // debug: [3 roles][64 tiles][8 slots] SM-clock stamps of CTA (0,0,0), or null
+  int handoff;             // v2: softmax groups alternate in the exponential loop (F5_ATTN_HANDOFF=0 disables)
+  unsigned long long* prof;  // in-graph timing slot (ptx.cuh prof_stamp_*), or null
+  int out_fp8;             // v2: `out` receives e4m3 bytes (ldo in bytes) — the A operand of an FP8-mode out-projection
+};
+
 
 struct Attn2Smem {
   static constexpr int kQ = 0;                        // 2 x (128 x 64 bf16)
