@@ -67,6 +67,7 @@ static int attention_impl(const void* qkv, int64_t ld_qkv, void* out, int64_t ld
     return 0;
   };
   const dim3 grid256(cdiv(frames, 256), heads, batch);
-  static SmemAttrOnce o4;
-  return launch(attn2_fwd_kernel<true, 0>, o4, grid256, 384, Attn2Smem::kTotal);
+  static SmemAttrOnce o4, o8;
+  if (out_fp8) return launch(attn2_fwd_kernel<true, 0, true>, o8, grid256, 384, Attn2Smem::kTotal);
+  return launch(attn2_fwd_kernel<true, 0, false>, o4, grid256, 384, Attn2Smem::kTotal);
 }

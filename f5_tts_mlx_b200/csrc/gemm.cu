@@ -7,11 +7,11 @@
 
 namespace f5 {
 
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const GemmParams& p, dim3 grid, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages>;
-  auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
+  auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE, FP8>;
   static SmemAttrOnce once;  // per instantiation
   F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
   const double taps = p.conv_taps;
@@ -30,8 +30,18 @@ template <int BN, int kStages>
 static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta,
                         const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const GemmParams& p,
                         dim3 grid, cudaStream_t stream) {
+  const bool fp8 = p.ab8 || p.out_fp8 || p.out2_fp8;     // e4m3 features: separate instantiations (what the FP8 mode of the DiT uses)
+#define F5_CASE8(A, O, R) \
+  if (fp8 && act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R, true>(ta, tb, to, to2, p, grid, stream);
+  F5_CASE8(ACT_NONE, true, true)
+  F5_CASE8(ACT_NONE, true, false)
+  F5_CASE8(ACT_NONE, false, false)
+  F5_CASE8(ACT_GELU_TANH, true, false)
+  F5_CASE8(ACT_MISH, false, false)
+#undef F5_CASE8
+  if (fp8) return set_error(F5_ERR_INVALID, "f5_gemm_bf16: FP8 features are not built for epilogue act=%d out_bf16=%d rope=%d", act, (int)out_bf16, (int)rope);
 #define F5_CASE(A, O, R) \
-  if (act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R>(ta, tb, to, to2, p, grid, stream);
+  if (act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R, false>(ta, tb, to, to2, p, grid, stream);
   F5_CASE(ACT_NONE, true, true)
   F5_CASE(ACT_NONE, true, false)
   F5_CASE(ACT_NONE, false, false)
@@ -44,11 +54,11 @@ static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta
                    act, (int)out_bf16, (int)rope);
 }
 
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                         const GemmParams& p, int n_tiles, int total_tiles, cudaStream_t stream) {
   using S = Gemm2Smem<BN, kStages, Gemm2Lno<BN, OUT_BF16>::value>;
-  auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE>;
+  auto kern = gemm2_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE, FP8>;
   static SmemAttrOnce once;
   F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
   const int num_pairs = sm_count() / 2;
@@ -69,8 +79,18 @@ template <int BN, int kStages>
 static int dispatch_epi2(int act, bool out_bf16, bool rope, const CUtensorMap& ta,
                          const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const GemmParams& p,
                          int n_tiles, int total_tiles, cudaStream_t stream) {
+  const bool fp8 = p.ab8 || p.out_fp8 || p.out2_fp8;
+#define F5_CASE8(A, O, R) \
+  if (fp8 && act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R, true>(ta, tb, to, to2, p, n_tiles, total_tiles, stream);
+  F5_CASE8(ACT_NONE, true, true)
+  F5_CASE8(ACT_NONE, true, false)
+  F5_CASE8(ACT_NONE, false, false)
+  F5_CASE8(ACT_GELU_TANH, true, false)
+  F5_CASE8(ACT_MISH, false, false)
+#undef F5_CASE8
+  if (fp8) return set_error(F5_ERR_INVALID, "f5_gemm_bf16: FP8 features are not built for epilogue act=%d out_bf16=%d rope=%d", act, (int)out_bf16, (int)rope);
 #define F5_CASE(A, O, R) \
-  if (act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R>(ta, tb, to, to2, p, n_tiles, total_tiles, stream);
+  if (act == A && out_bf16 == O && rope == R) return launch_gemm2<BN, kStages, A, O, R, false>(ta, tb, to, to2, p, n_tiles, total_tiles, stream);
   F5_CASE(ACT_NONE, true, true)
   F5_CASE(ACT_NONE, true, false)
   F5_CASE(ACT_NONE, false, false)

@@ -19,6 +19,8 @@
 //           accumulator stage i while the MMAs fill stage i^1, then arrive on the leader's tmem_empty barrier;
 //           setmaxnreg hands registers from warps 0-3 (40) to the epilogue warps (232)
 #pragma once
+#include <type_traits>
+
 #include "gemm_epilogue.cuh"
 
 namespace f5 {
@@ -150,12 +152,14 @@ struct Gemm2Lno {
   static constexpr bool value = !OUT_BF16 && BN == 256;
 };
 
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                      const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
-                     const __grid_constant__ CUtensorMap tma_out2, const GemmParams p,
+                     const __grid_constant__ CUtensorMap tma_out2, const GemmParams p_arg,
                      const int n_tiles, const int total_tiles) {
+  GemmParams p = p_arg;      // FP8 = false: the e4m3 features are compile-time off (see gemm_sm100.cuh)
+  if constexpr (!FP8) { p.ab8 = 0; p.out_fp8 = 0; p.out2_fp8 = 0; p.acc_scale = 1.f; }
   constexpr bool LNO = Gemm2Lno<BN, OUT_BF16>::value;
   using S = Gemm2Smem<BN, kStages, LNO>;
   extern __shared__ uint8_t smem_raw[];
@@ -226,70 +230,111 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
-      int kcount = 0;
-      for (int i = 0, t = walk.first; i < walk.count; ++i, t += walk.stride) {
-        const int n_tile = t % n_tiles, m_tile = t / n_tiles;
-        const int n0 = n_tile * BN;
-        int batch = 0, m_in_batch0;
-        if (pair_tiles_per_batch > 0) {
-          batch = m_tile / pair_tiles_per_batch;
-          m_in_batch0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
-        } else {
-          m_in_batch0 = m_tile * 256 + (int)rank * 128;
+      auto produce = [&](auto ab8_tag) {
+        constexpr int KBE = decltype(ab8_tag)::value ? 128 : 64;     // elements per k-block, compile-time in the loop
+        int kcount = 0;
+        for (int i = 0, t = walk.first; i < walk.count; ++i, t += walk.stride) {
+          const int n_tile = t % n_tiles, m_tile = t / n_tiles;
+          const int n0 = n_tile * BN;
+          int batch = 0, m_in_batch0;
+          if (pair_tiles_per_batch > 0) {
+            batch = m_tile / pair_tiles_per_batch;
+            m_in_batch0 = (m_tile % pair_tiles_per_batch) * 256 + (int)rank * 128;
+          } else {
+            m_in_batch0 = m_tile * 256 + (int)rank * 128;
+          }
+          for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
+            const int s = kcount % kStages;
+            const uint32_t ph = (kcount / kStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * S::kStageBytes;
+            uint8_t* sb = sa + S::kABytes;
+            const bool early = kcount < early_b;   // B tile and expect_tx already issued before the PDL wait
+            if (rank == 0 && !early) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+            const int tap = kb / kb_per_tap;
+            const int kc = kb - tap * kb_per_tap;
+            const int a_col = (p.conv_grouped ? n0 : 0) + kc * KBE;
+            tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
+            if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * KBE, n0 + (int)rank * (BN / 2));
+            if (kcount == 0) ts_mark(p, blockIdx.x, 3);
+          }
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
-          const int s = kcount % kStages;
-          const uint32_t ph = (kcount / kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
-          const bool early = kcount < early_b;   // B tile and expect_tx already issued before the PDL wait
-          if (rank == 0 && !early) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-          const int tap = kb / kb_per_tap;
-          const int kc = kb - tap * kb_per_tap;
-          const int a_col = (p.conv_grouped ? n0 : 0) + kc * kbe;
-          tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
-          if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * kbe, n0 + (int)rank * (BN / 2));
-          if (kcount == 0) ts_mark(p, blockIdx.x, 3);
-        }
-      }
+      };
+      if (p.ab8) produce(std::true_type{});
+      else produce(std::false_type{});
       ts_mark(p, blockIdx.x, 4);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
-      constexpr uint32_t idesc8 = umma_idesc_e4m3(256, BN);
-      const bool ab8 = p.ab8 != 0;
-      int kcount = 0, acount = 0;
-      for (int i = 0; i < walk.count; ++i, ++acount) {
-        const int as = acount & 1;
-        const uint32_t aph = (acount >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[as], aph ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
-          const int s = kcount % kStages;
-          const uint32_t ph = (kcount / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          if (lane == 0) {
-            if (kcount == 0) ts_mark(p, blockIdx.x, 5);
-            const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-            const uint32_t sb = sa + S::kABytes;
+      // operand kind resolved once, outside the issue loop (see gemm_sm100.cuh)
+      auto mma_loop = [&](auto ab8_tag) {
+        constexpr bool AB8 = decltype(ab8_tag)::value;
+        constexpr uint32_t idesc = AB8 ? umma_idesc_e4m3(256, BN) : umma_idesc_bf16(256, BN, 0, 0);
+#if F5_ISSUE1
+        if (lane == 0) {
+          const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+          const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
+          int acount = 0, s = 0;
+          uint32_t ph = 0;
+          uint64_t da = da0, db = db0;
+          constexpr uint64_t kStageInc = (uint64_t)(S::kStageBytes >> 4);
+          bool first = true;
+          for (int i = 0; i < walk.count; ++i, ++acount) {
+            const int as = acount & 1;
+            const uint32_t aph = (acount >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+              mbar_wait(&full_bar[s], ph);
+              tc_fence_after();
+              if (first) { ts_mark(p, blockIdx.x, 5); first = false; }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
-              uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-              if (ab8) umma_f8_ss_2sm(tmem_acc, da, db, idesc8, (kb | k) != 0);
-              else umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if constexpr (AB8) umma_f8_ss_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                else umma_f16_ss_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              }
+              tc_commit_2sm(&empty_bar[s], 3);
+              if (++s == kStages) { s = 0; ph ^= 1; da = da0; db = db0; } else { da += kStageInc; db += kStageInc; }
             }
-            tc_commit_2sm(&empty_bar[s], 3);
-            if (kb == num_kb - 1) tc_commit_2sm(&tmem_full_bar[as], 3);
+            tc_commit_2sm(&tmem_full_bar[as], 3);
           }
-          __syncwarp();
         }
-      }
+#else
+        int kcount = 0, acount = 0;
+        for (int i = 0; i < walk.count; ++i, ++acount) {
+          const int as = acount & 1;
+          const uint32_t aph = (acount >> 1) & 1;
+          mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + as * BN;
+          for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
+            const int s = kcount % kStages;
+            const uint32_t ph = (kcount / kStages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+              if (kcount == 0) ts_mark(p, blockIdx.x, 5);
+              const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+              const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+                uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+                if constexpr (AB8) umma_f8_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+                else umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+              }
+              tc_commit_2sm(&empty_bar[s], 3);
+              if (kb == num_kb - 1) tc_commit_2sm(&tmem_full_bar[as], 3);
+            }
+            __syncwarp();
+          }
+        }
+#endif
+      };
+      if (p.ab8) mma_loop(std::true_type{});
+      else mma_loop(std::false_type{});
       if (lane == 0) ts_mark(p, blockIdx.x, 6);
     }
   }

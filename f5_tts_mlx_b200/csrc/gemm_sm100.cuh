@@ -25,6 +25,12 @@
 //   v += resid[row, col]                                  residual (fp32 stream)
 //   store fp32 or bf16
 #pragma once
+#include <type_traits>
+
+#ifndef F5_ISSUE1
+#define F5_ISSUE1 1
+#endif
+
 #include "ptx.cuh"
 #include "gemm_epilogue.cuh"
 
@@ -55,11 +61,16 @@ struct GemmEpi {
   static constexpr int kCols = BN / kGroups;          // columns per group
 };
 
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE>
+// FP8 = false instantiations have every e4m3 feature (ab8 / out_fp8 / out2_fp8 / acc_scale) folded away at compile
+// time: the prologue, the issue loop and the epilogue are sensitive to every extra instruction (r02: carrying the
+// run-time flags cost the bf16 path 1-3 % of the step), so only the FP8 mode pays for the FP8 mode.
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8 = false>
 __global__ void __launch_bounds__(GemmEpi<BN, kStages>::kThreads, (kStages > 4) ? 1 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
-                    const __grid_constant__ CUtensorMap tma_out2, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tma_out2, const GemmParams p_arg) {
+  GemmParams p = p_arg;
+  if constexpr (!FP8) { p.ab8 = 0; p.out_fp8 = 0; p.out2_fp8 = 0; p.acc_scale = 1.f; }
   using S = GemmSmem<BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
@@ -128,56 +139,95 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * S::kStageBytes;
-        uint8_t* sb = sa + S::kABytes;
-        if (kb >= early_b) mbar_expect_tx(&full_bar[s], S::kStageBytes);
-        const int tap = kb / kb_per_tap;
-        const int kc = kb - tap * kb_per_tap;
-        const int a_col = (p.conv_grouped ? n0 : 0) + kc * kbe;
-        tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
-                    p.tiles_per_batch > 0 ? batch : 0);
-        if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * kbe, n0);
+      auto produce = [&](auto ab8_tag) {
+        constexpr int KBE = decltype(ab8_tag)::value ? 128 : 64;     // elements per k-block, compile-time in the loop
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb % kStages;
+          const uint32_t ph = (kb / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          if (kb >= early_b) mbar_expect_tx(&full_bar[s], S::kStageBytes);
+          const int tap = kb / kb_per_tap;
+          const int kc = kb - tap * kb_per_tap;
+          const int a_col = (p.conv_grouped ? n0 : 0) + kc * KBE;
+          tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
+                      p.tiles_per_batch > 0 ? batch : 0);
+          if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * KBE, n0);
 #ifndef F5_EPI_PROBE
-        if (kb == 0) ts_mark(p, cta_lin, 3);
+          if (kb == 0) ts_mark(p, cta_lin, 3);
 #endif
-      }
+        }
+      };
+      if (p.ab8) produce(std::true_type{});
+      else produce(std::false_type{});
 #ifndef F5_EPI_PROBE
       ts_mark(p, cta_lin, 4);
 #endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    constexpr uint32_t idesc8 = umma_idesc_e4m3(128, BN);
-    const bool ab8 = p.ab8 != 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (kb / kStages) & 1;
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
+    // The issue loop is the GEMM's critical resource (r02: a run-time branch per MMA between the bf16 and the e4m3
+    // instruction cost 15 % of the whole step), so the operand kind is resolved ONCE, outside the loop.
+    auto mma_loop = [&](auto ab8_tag) {
+      constexpr bool AB8 = decltype(ab8_tag)::value;
+      constexpr uint32_t idesc = AB8 ? umma_idesc_e4m3(128, BN) : umma_idesc_bf16(128, BN, 0, 0);
+#if F5_ISSUE1
+      // one thread runs the whole loop (no warp-wide barrier polling / reconvergence per k-block); the two operand
+      // descriptors of a stage differ from stage 0's by a constant, and the four K-steps by 32 bytes (>> 4 = 2)
       if (lane == 0) {
-        if (kb == 0) ts_mark(p, cta_lin, 5);
-        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+        const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
+        // stage index / phase / descriptors advance by increments (no % or / by the non-power-of-two stage count in
+        // the loop: every instruction between two MMAs of this thread is time the tensor pipe may sit idle)
+        int s = 0;
+        uint32_t ph = 0;
+        uint64_t da = da0, db = db0;
+        constexpr uint64_t kStageInc = (uint64_t)(S::kStageBytes >> 4);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (kb == 0) ts_mark(p, cta_lin, 5);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K(16) per 64-wide k-block; +32 B per step
-          uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
-          uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-          if (ab8) umma_f8_ss(tmem_base, da, db, idesc8, (kb | k) != 0);   // 32 e4m3 per instruction = the same 32 bytes
-          else umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            if constexpr (AB8) umma_f8_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);
+          if (++s == kStages) { s = 0; ph ^= 1; da = da0; db = db0; } else { da += kStageInc; db += kStageInc; }
         }
-        tc_commit(&empty_bar[s]);                        // frees the smem slot when MMAs retire
-        if (kb == num_kb - 1) {
-          tc_commit(tmem_full_bar);  // accumulator complete
-          ts_mark(p, cta_lin, 6);
-        }
+        tc_commit(tmem_full_bar);     // accumulator complete (commits track every MMA issued before)
+        ts_mark(p, cta_lin, 6);
       }
-      __syncwarp();
-    }
+#else
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          if (kb == 0) ts_mark(p, cta_lin, 5);
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x UMMA_K (16 bf16 / 32 e4m3 = 32 bytes) per 128-byte k-block row
+            uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+            uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
+            if constexpr (AB8) umma_f8_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+            else umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);                        // frees the smem slot when MMAs retire
+          if (kb == num_kb - 1) {
+            tc_commit(tmem_full_bar);  // accumulator complete
+            ts_mark(p, cta_lin, 6);
+          }
+        }
+        __syncwarp();
+      }
+#endif
+    };
+    if (p.ab8) mma_loop(std::true_type{});
+    else mma_loop(std::false_type{});
   } else {
     // ===================== epilogue =====================
     using E = GemmEpi<BN, kStages>;
