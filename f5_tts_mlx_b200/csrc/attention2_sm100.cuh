@@ -101,7 +101,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
     if (probe && j < 64) p.ts[(role * 64 + j) * 8 + slot] = (unsigned long long)clock64();
   };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && F5_ELECT_LANE()) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -131,7 +131,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (F5_ELECT_LANE()) {
       mbar_expect_tx(q_full, g1_active ? 32768 : 16384);
       tma_load_3d(smem + Attn2Smem::kQ, &tma_qkv, q_full, h * 64, q0, b);
       if (g1_active) tma_load_3d(smem + Attn2Smem::kQ + 16384, &tma_qkv, q_full, h * 64, q0 + 128, b);
@@ -182,7 +182,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      if (lane == 0) {
+      if (F5_ELECT_LANE()) {
         issue_S(0);
         tc_commit(&s_full[g]);
         tc_commit(&k_empty[0]);
@@ -197,7 +197,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
           mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
           mbar_wait(&s_free[g], j & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (F5_ELECT_LANE()) {
             stamp(2, j, g);
             issue_S(s ^ 1);
             tc_commit(&s_full[g]);
@@ -208,7 +208,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
         mbar_wait(&v_full[s], ph);
         mbar_wait(&p_full[g], j & 1);
         tc_fence_after();
-        if (lane == 0) {
+        if (F5_ELECT_LANE()) {
           stamp(2, j, 3 + g);
           issue_PV(s, j > 0);
           tc_commit(&pv_done[g]);

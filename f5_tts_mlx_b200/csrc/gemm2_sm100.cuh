@@ -76,6 +76,13 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t mask) {
       "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tc_commit_2sm_u32(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
 // TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                                 int c0, int c1) {
@@ -183,7 +190,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   const TileWalk walk = tile_walk(cluster_id, num_clusters, n_tiles, total_tiles);
 
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 0);
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && F5_ELECT_LANE()) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
@@ -210,7 +217,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (threadIdx.x == 0) ts_mark(p, blockIdx.x, 1);
   // first ring of B (weight) tiles of this cluster's first tile: requested before the PDL wait (gemm_sm100.cuh)
   const int early_b = (p.w_static && walk.count > 0) ? min(kStages, num_kb) : 0;
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && F5_ELECT_LANE()) {
     const int n0e = (walk.first % n_tiles) * BN;
     for (int kb = 0; kb < early_b; ++kb) {
       if (rank == 0) mbar_expect_tx(&full_bar[kb], 2 * S::kStageBytes);
@@ -229,10 +236,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (F5_ELECT_LANE()) {
       auto produce = [&](auto ab8_tag) {
         constexpr int KBE = decltype(ab8_tag)::value ? 128 : 64;     // elements per k-block, compile-time in the loop
-        int kcount = 0;
+        // incremental stage / phase / tap bookkeeping: no division in the k loop (see gemm_sm100.cuh)
+        int kcount = 0, s = 0;
+        uint32_t ph = 1;
+        uint8_t* sa = smem;
+        const int b_row = (int)rank * (BN / 2);
         for (int i = 0, t = walk.first; i < walk.count; ++i, t += walk.stride) {
           const int n_tile = t % n_tiles, m_tile = t / n_tiles;
           const int n0 = n_tile * BN;
@@ -243,20 +254,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
           } else {
             m_in_batch0 = m_tile * 256 + (int)rank * 128;
           }
+          const int a_col0 = p.conv_grouped ? n0 : 0;
+          const int a_row0 = m_in_batch0 - p.conv_pad;
+          int tap = 0, kc = 0;
           for (int kb = 0; kb < num_kb; ++kb, ++kcount) {
-            const int s = kcount % kStages;
-            const uint32_t ph = (kcount / kStages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * S::kStageBytes;
-            uint8_t* sb = sa + S::kABytes;
+            mbar_wait(&empty_bar[s], ph);
             const bool early = kcount < early_b;   // B tile and expect_tx already issued before the PDL wait
             if (rank == 0 && !early) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-            const int tap = kb / kb_per_tap;
-            const int kc = kb - tap * kb_per_tap;
-            const int a_col = (p.conv_grouped ? n0 : 0) + kc * KBE;
-            tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad, batch);
-            if (!early) tma_load_2d_2sm(sb, &tma_b, &full_bar[s], kb * KBE, n0 + (int)rank * (BN / 2));
+            tma_load_3d_2sm(sa, &tma_a, &full_bar[s], a_col0 + kc * KBE, a_row0 + tap, batch);
+            if (!early) tma_load_2d_2sm(sa + S::kABytes, &tma_b, &full_bar[s], kb * KBE, n0 + b_row);
             if (kcount == 0) ts_mark(p, blockIdx.x, 3);
+            if (++s == kStages) { s = 0; ph ^= 1; sa = smem; } else { sa += S::kStageBytes; }
+            if (++kc == kb_per_tap) { kc = 0; ++tap; }
           }
         }
       };
@@ -272,33 +281,40 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
         constexpr bool AB8 = decltype(ab8_tag)::value;
         constexpr uint32_t idesc = AB8 ? umma_idesc_e4m3(256, BN) : umma_idesc_bf16(256, BN, 0, 0);
 #if F5_ISSUE1
-        if (lane == 0) {
-          const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
-          const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
-          int acount = 0, s = 0;
+        if (F5_ELECT_LANE()) {
+          // one running 32-bit descriptor word and one running barrier address (gemm_sm100.cuh); this warp lives on 40
+          // registers, and a spilled loop variable is a local-memory round trip between two MMAs
+          constexpr uint32_t kHi = (uint32_t)(umma_desc_sw128(0, 16, 1024) >> 32);
+          constexpr uint32_t kStageInc = S::kStageBytes >> 4, kBOff = S::kABytes >> 4;
+          uint32_t a_lo = (uint32_t)umma_desc_sw128(smem_u32(smem), 16, 1024);
+          uint32_t bar = smem_u32(full_bar);       // full_bar[s]; empty_bar[s] is kStages * 8 bytes behind
+          const uint32_t acc_bar = smem_u32(tmem_full_bar);   // tmem_full_bar[as]; tmem_empty_bar[as] 16 bytes behind
+          int s = 0;
           uint32_t ph = 0;
-          uint64_t da = da0, db = db0;
-          constexpr uint64_t kStageInc = (uint64_t)(S::kStageBytes >> 4);
-          bool first = true;
-          for (int i = 0; i < walk.count; ++i, ++acount) {
-            const int as = acount & 1;
-            const uint32_t aph = (acount >> 1) & 1;
-            mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+          if (walk.count > 0 && num_kb > 0) {      // first stage has landed: stamp outside the loops
+            mbar_wait_u32(bar, 0);
+            ts_mark(p, blockIdx.x, 5);
+          }
+          for (int i = 0; i < walk.count; ++i) {
+            const uint32_t as = i & 1;
+            mbar_wait_u32(acc_bar + 16 + as * 8, ((i >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + as * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
-              mbar_wait(&full_bar[s], ph);
+              mbar_wait_u32(bar, ph);
               tc_fence_after();
-              if (first) { ts_mark(p, blockIdx.x, 5); first = false; }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if constexpr (AB8) umma_f8_ss_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                else umma_f16_ss_2sm(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                const uint64_t da = umma_desc_words(a_lo + 2 * k, kHi);
+                const uint64_t db = umma_desc_words(a_lo + kBOff + 2 * k, kHi);
+                if constexpr (AB8) umma_f8_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
+                else umma_f16_ss_2sm(tmem_acc, da, db, idesc, (kb | k) != 0);
               }
-              tc_commit_2sm(&empty_bar[s], 3);
-              if (++s == kStages) { s = 0; ph ^= 1; da = da0; db = db0; } else { da += kStageInc; db += kStageInc; }
+              tc_commit_2sm_u32(bar + kStages * 8, 3);
+              if (++s == kStages) { s = 0; ph ^= 1; a_lo -= (kStages - 1) * kStageInc; bar -= (kStages - 1) * 8; }
+              else { a_lo += kStageInc; bar += 8; }
             }
-            tc_commit_2sm(&tmem_full_bar[as], 3);
+            tc_commit_2sm_u32(acc_bar + as * 8, 3);
           }
         }
 #else
@@ -335,7 +351,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       };
       if (p.ab8) mma_loop(std::true_type{});
       else mma_loop(std::false_type{});
-      if (lane == 0) ts_mark(p, blockIdx.x, 6);
+      if (F5_ELECT_LANE()) ts_mark(p, blockIdx.x, 6);
     }
   }
   } else {

@@ -102,7 +102,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   // ---- one-time setup (overlaps the predecessor kernel under PDL) ----
   const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
   if (threadIdx.x == 0) ts_mark(p, cta_lin, 0);
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && F5_ELECT_LANE()) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_out);
@@ -127,7 +127,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   // weights do not depend on the predecessor kernel: the first ring of B tiles is requested BEFORE the PDL
   // wait, so their (possibly HBM) latency runs under the predecessor's tail
   const int early_b = p.w_static ? min(kStages, num_kb) : 0;
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && F5_ELECT_LANE()) {
     for (int kb = 0; kb < early_b; ++kb) {
       mbar_expect_tx(&full_bar[kb], S::kStageBytes);
       tma_load_2d(smem + kb * S::kStageBytes + S::kABytes, &tma_b, &full_bar[kb], kb * kbe, n0);
@@ -138,25 +138,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (F5_ELECT_LANE()) {
       auto produce = [&](auto ab8_tag) {
         constexpr int KBE = decltype(ab8_tag)::value ? 128 : 64;     // elements per k-block, compile-time in the loop
+        // incremental stage / phase / tap bookkeeping: no division in the loop (see the issue loop below)
+        int s = 0, tap = 0, kc = 0;
+        uint32_t ph = 1;
+        uint8_t* sa = smem;
+        const int a_col0 = p.conv_grouped ? n0 : 0;
+        const int a_row0 = m_in_batch0 - p.conv_pad;
+        const int a_b = p.tiles_per_batch > 0 ? batch : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          const int s = kb % kStages;
-          const uint32_t ph = (kb / kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
+          mbar_wait(&empty_bar[s], ph);
           if (kb >= early_b) mbar_expect_tx(&full_bar[s], S::kStageBytes);
-          const int tap = kb / kb_per_tap;
-          const int kc = kb - tap * kb_per_tap;
-          const int a_col = (p.conv_grouped ? n0 : 0) + kc * KBE;
-          tma_load_3d(sa, &tma_a, &full_bar[s], a_col, m_in_batch0 + tap - p.conv_pad,
-                      p.tiles_per_batch > 0 ? batch : 0);
-          if (kb >= early_b) tma_load_2d(sb, &tma_b, &full_bar[s], kb * KBE, n0);
+          tma_load_3d(sa, &tma_a, &full_bar[s], a_col0 + kc * KBE, a_row0 + tap, a_b);
+          if (kb >= early_b) tma_load_2d(sa + S::kABytes, &tma_b, &full_bar[s], kb * KBE, n0);
 #ifndef F5_EPI_PROBE
           if (kb == 0) ts_mark(p, cta_lin, 3);
 #endif
+          if (++s == kStages) { s = 0; ph ^= 1; sa = smem; } else { sa += S::kStageBytes; }
+          if (++kc == kb_per_tap) { kc = 0; ++tap; }
         }
       };
       if (p.ab8) produce(std::true_type{});
@@ -175,26 +176,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
 #if F5_ISSUE1
       // one thread runs the whole loop (no warp-wide barrier polling / reconvergence per k-block); the two operand
       // descriptors of a stage differ from stage 0's by a constant, and the four K-steps by 32 bytes (>> 4 = 2)
-      if (lane == 0) {
-        const uint64_t da0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
-        const uint64_t db0 = umma_desc_sw128(smem_u32(smem) + S::kABytes, 16, 1024);
-        // stage index / phase / descriptors advance by increments (no % or / by the non-power-of-two stage count in
-        // the loop: every instruction between two MMAs of this thread is time the tensor pipe may sit idle)
+      if (F5_ELECT_LANE()) {
+        // stage index / phase / descriptor advance by increments (no % or / by the non-power-of-two stage count in
+        // the loop: every instruction between two MMAs of this thread is time the tensor pipe may sit idle).  One
+        // running 32-bit descriptor word: B's tile sits kABytes behind A's, a K-step is 32 bytes (>> 4 = 2).
+        constexpr uint32_t kHi = (uint32_t)(umma_desc_sw128(0, 16, 1024) >> 32);
+        constexpr uint32_t kStageInc = S::kStageBytes >> 4, kBOff = S::kABytes >> 4;
+        uint32_t a_lo = (uint32_t)umma_desc_sw128(smem_u32(smem), 16, 1024);
+        uint32_t bar = smem_u32(full_bar);       // full_bar[s]; empty_bar[s] is kStages * 8 bytes behind
         int s = 0;
         uint32_t ph = 0;
-        uint64_t da = da0, db = db0;
-        constexpr uint64_t kStageInc = (uint64_t)(S::kStageBytes >> 4);
+        if (num_kb > 0) mbar_wait_u32(bar, 0);   // first stage has landed: stamp outside the loop
+        ts_mark(p, cta_lin, 5);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait_u32(bar, ph);
           tc_fence_after();
-          if (kb == 0) ts_mark(p, cta_lin, 5);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if constexpr (AB8) umma_f8_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            const uint64_t da = umma_desc_words(a_lo + 2 * k, kHi), db = umma_desc_words(a_lo + kBOff + 2 * k, kHi);
+            if constexpr (AB8) umma_f8_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+            else umma_f16_ss(tmem_base, da, db, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[s]);
-          if (++s == kStages) { s = 0; ph ^= 1; da = da0; db = db0; } else { da += kStageInc; db += kStageInc; }
+          tc_commit_u32(bar + kStages * 8);
+          if (++s == kStages) { s = 0; ph ^= 1; a_lo -= (kStages - 1) * kStageInc; bar -= (kStages - 1) * 8; }
+          else { a_lo += kStageInc; bar += 8; }
         }
         tc_commit(tmem_full_bar);     // accumulator complete (commits track every MMA issued before)
         ts_mark(p, cta_lin, 6);

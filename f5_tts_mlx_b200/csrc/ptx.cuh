@@ -30,6 +30,18 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// One thread of a CONVERGED warp.  Choosing it with elect.sync instead of `lane == 0` matters for code size in the
+// single-thread TMA / tcgen05 loops: under `lane == 0` the compiler wraps every UTCHMMA / UTMALDG / UTCBAR in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY serialisation loop (7 instructions per MMA); under elect.sync they issue
+// back to back.  F5_ELECT_MODE=0 restores lane 0 for A/B measurements.
+#ifndef F5_ELECT_MODE
+#define F5_ELECT_MODE 1
+#endif
+#if F5_ELECT_MODE
+#define F5_ELECT_LANE() ::f5::elect_one()
+#else
+#define F5_ELECT_LANE() (lane == 0)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
@@ -102,6 +114,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0x3ff) == 0 && (clock64() - t0) > 4000000000LL) {
       printf("f5: mbarrier wait timeout (block %d,%d thread %d parity %u)\n", blockIdx.x,
              blockIdx.y, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// The same bounded wait for the single-thread issue / producer loops, on a 32-bit shared address: those warps run on
+// a 40-register budget (setmaxnreg) and every spill in them sits between two MMAs, so the time-out keeps a 32-bit
+// clock and reports out of line.
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout_report(uint32_t bar, uint32_t parity) {
+  printf("f5: mbarrier wait timeout (block %d,%d thread %d barrier 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+         threadIdx.x, bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_u32(bar, parity)) return;
+  const uint32_t t0 = (uint32_t)clock();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_u32(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && (uint32_t)((uint32_t)clock() - t0) > 3500000000u) {   // ~1.8 s
+      mbar_timeout_report(bar, parity);
       __trap();
     }
   }
@@ -184,6 +226,9 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
           smem_u32(bar))
       : "memory");
+}
+__device__ __forceinline__ void tc_commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
@@ -277,7 +322,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // MN-major operand (e.g. V[kv][d] used as B with N=d contiguous, 64 elements = one 128 B
 // swizzle span): 8 k-rows per 1024 B atom; SBO = 1024 B between k-groups; LBO = distance between
 // 64-element MN chunks (unused when the MN extent is 64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
+__host__ __device__ constexpr uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
                                                     uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -286,6 +331,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)1 << 46;  // version
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
+}
+
+// The descriptor as two words: the high one (SBO, version, swizzle mode) is a compile-time constant of the layout, the
+// low one carries the start address (>> 4, 14 bits: adding a byte offset >> 4 never carries out of it).  The
+// single-thread issue loops keep ONE running 32-bit word per operand ring instead of 64-bit descriptors.
+__device__ __forceinline__ uint64_t umma_desc_words(uint32_t lo, uint32_t hi) {
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
