@@ -5,6 +5,12 @@
 #include "gemm2_sm100.cuh"
 #include "host_common.h"
 
+// operand-ring depth of the one-CTA-per-SM kernel: the main loop is bound by bytes in flight / TMA latency (r02: the
+// same 400 clk per k-block with 8 or 120 CTAs running), so the ring takes all the shared memory there is
+#ifndef F5_ONEWAVE_STAGES
+#define F5_ONEWAVE_STAGES 6
+#endif
+
 namespace f5 {
 
 template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8>
@@ -321,7 +327,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   // grids that fit in one wave leave one CTA per SM anyway: spend the whole smem on a 6-stage ring
   // (192 KB in flight per SM instead of 96 KB) to cover the L2/HBM latency of the operand stream
   if (bn == 128 && (long long)grid.x * grid.y <= sm_count())
-    return dispatch_epi<128, 6>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
+    return dispatch_epi<128, F5_ONEWAVE_STAGES>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
   if (bn == 128) return dispatch_epi<128, 3>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
   return dispatch_epi<64, 4>(a->act, a->out_bf16 != 0, rope, ta, tb, to, to2, p, grid, stream);
 }

@@ -170,8 +170,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   constexpr bool LNO = Gemm2Lno<BN, OUT_BF16>::value;
   using S = Gemm2Smem<BN, kStages, LNO>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
+  // emits LDS / STS instead of generic LD / ST for everything derived from `smem`)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
@@ -414,6 +415,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.et = et;
       stg.bar_id = 1 + grp;
       stg.probe_cta = blockIdx.x;
+      stg.probe = p.ts != nullptr ? p.ts + (size_t)blockIdx.x * 10 : nullptr;
       stg.r = lg * 32 + lane;
       stg.buf2 = LNO ? smem + S::kStage2Offset + grp * 8192 : nullptr;
       stg.buf2_par = 0;

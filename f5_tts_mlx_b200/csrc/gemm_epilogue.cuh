@@ -206,6 +206,7 @@ struct EpiStage {
   int r;                   // this thread's row inside the tile
   int bar_id;              // named barrier of this group of 4 epilogue warps (1 + group)
   int probe_cta;           // debug (F5_EPI_PROBE builds): linear CTA id for sub-step stamps
+  unsigned long long* probe;   // debug: this CTA's timeline row (GemmParams::ts + 10 * cta) or nullptr
   const CUtensorMap* map_out;   // (cols, rows per utterance, utterances) of `out` / `out2`
   const CUtensorMap* map_out2;
   int c1, c2;              // tensor-map coordinates of tile row 0: row inside the utterance, utterance
@@ -214,6 +215,21 @@ struct EpiStage {
   float mu_r, rstd;        // fused-LN consumer mode: this thread's row statistics ((0, 1) otherwise)
 };
 
+// Sub-step stamps of the first epilogue group's thread 0 (debug builds -DF5_EPI_PROBE=1..5, slots 3 and 4 of the
+// per-CTA timeline, which the producer leaves free in those builds): which part of a chunk's latency chain costs what.
+#ifdef F5_EPI_PROBE
+#define F5_EPI_MARK(level, cond, slot)                                                              \
+  do {                                                                                              \
+    if (F5_EPI_PROBE == (level) && st.probe != nullptr && st.et == 0 && st.bar_id == 1 && (cond)) { \
+      unsigned long long t_;                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+      st.probe[slot] = t_;                                                                          \
+    }                                                                                               \
+  } while (0)
+#else
+#define F5_EPI_MARK(level, cond, slot) do { } while (0)
+#endif
+
 // `w2`: the chunk's second output (bf16, 4 x uint4 per row) or nullptr
 // `w2_fp8`: the second output is e4m3 — 32-byte rows, SWIZZLE_32B (16-byte chunk index ^ bit 7 of the row offset)
 template <bool OUT_BF16>
@@ -221,6 +237,8 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
                                               const uint4* w2 = nullptr, bool w2_fp8 = false) {
   uint8_t* buf = st.buf + par * 16384;
   uint8_t* buf2 = st.buf2 + par * st.buf2_par;
+  F5_EPI_MARK(2, par == 0, 3);     // chunk 0: math done
+  F5_EPI_MARK(4, par == 1, 4);     // chunk 1: math done
 #if F5_EPI_WAIT_MODE == 1
   // two barriers per chunk: the buffer about to be rewritten was the source of the store before the previous one;
   // the previous chunk's store may still be in flight while this chunk is computed and staged
@@ -272,17 +290,23 @@ __device__ __forceinline__ void epi_store_tma(const float (&v)[32], const EpiSta
     }
   }
   fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA unit
+  F5_EPI_MARK(2, par == 0, 4);     // chunk 0: staged + fenced
 #if F5_EPI_WAIT_MODE != 1
   // the OTHER staging buffer is rewritten by the next chunk: every store issued so far must have read its source
   // (the previous chunk's store was issued a whole chunk of work ago)
   if (st.et == 0) tma_store_wait_read<0>();
 #endif
+  F5_EPI_MARK(3, par == 0, 3);     // chunk 0: previous store's reads done (none for chunk 0)
+  F5_EPI_MARK(5, par == 1, 3);     // chunk 1: chunk 0's store has read its staging buffer
   asm volatile("bar.sync %0, 128;" ::"r"(st.bar_id) : "memory");
+  F5_EPI_MARK(3, par == 0, 4);     // chunk 0: group barrier passed
   if (st.et == 0) {
     tma_store_3d(st.map_out, buf, col0, st.c1, st.c2);
     if (w2 != nullptr) tma_store_3d(st.map_out2, buf2, col0, st.c1, st.c2);
     tma_store_commit();
   }
+  F5_EPI_MARK(4, par == 0, 3);     // chunk 0: stores issued
+  F5_EPI_MARK(5, par == 1, 4);     // chunk 1: stores issued (epi_end - this = the final wait for the store's reads)
 }
 
 // HALF: which 32-column half of a 64-column head this chunk is (static RoPE register indexing)
@@ -297,15 +321,26 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
   float v[32];
   // rstd * acc - (mean * rstd) * c1 + (c2 + bias): the fused-LN consumer; (mu_r, rstd) = (0, 1) otherwise.
   // acc_scale (the e4m3 weight tensor's scale in FP8 mode, else 1) belongs to the accumulator term only.
-  const float ra = st.rstd * p.acc_scale;
+  if (p.ln_in_stats != nullptr) {          // uniform: only a fused-LN consumer pays for the mean term
+    const float ra = st.rstd * p.acc_scale;
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
-    const float4 cc = *reinterpret_cast<const float4*>(aux_s + j);
-    v[j] = fmaf(__uint_as_float(acc[j]), ra, fmaf(-st.mu_r, cc.x, bb.x));
-    v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), ra, fmaf(-st.mu_r, cc.y, bb.y));
-    v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), ra, fmaf(-st.mu_r, cc.z, bb.z));
-    v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), ra, fmaf(-st.mu_r, cc.w, bb.w));
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+      const float4 cc = *reinterpret_cast<const float4*>(aux_s + j);
+      v[j] = fmaf(__uint_as_float(acc[j]), ra, fmaf(-st.mu_r, cc.x, bb.x));
+      v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), ra, fmaf(-st.mu_r, cc.y, bb.y));
+      v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), ra, fmaf(-st.mu_r, cc.z, bb.z));
+      v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), ra, fmaf(-st.mu_r, cc.w, bb.w));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bb = *reinterpret_cast<const float4*>(bias_s + j);
+      v[j] = fmaf(__uint_as_float(acc[j]), p.acc_scale, bb.x);
+      v[j + 1] = fmaf(__uint_as_float(acc[j + 1]), p.acc_scale, bb.y);
+      v[j + 2] = fmaf(__uint_as_float(acc[j + 2]), p.acc_scale, bb.z);
+      v[j + 3] = fmaf(__uint_as_float(acc[j + 3]), p.acc_scale, bb.w);
+    }
   }
   if (ACT == ACT_GELU_TANH) {
 #pragma unroll
@@ -359,10 +394,14 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
       // second output: bf16(v * aux) — the fused-LN operand x * (1 + s) of the GEMM that consumes LN(x) (aux = 1 when
       // no ln_scale is given: a plain bf16 copy); with ln_stats also the unit statistics of the finished row
       if (p.ln_stats != nullptr) {
-        float s1 = HALF == 0 ? 0.f : unit_acc.x, s2 = HALF == 0 ? 0.f : unit_acc.y;
+        // four partial sums each: a 32-long dependent add chain costs more than the rest of the chunk's arithmetic
+        float s1[4] = {HALF == 0 ? 0.f : unit_acc.x, 0.f, 0.f, 0.f}, s2[4] = {HALF == 0 ? 0.f : unit_acc.y, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
-        unit_acc = make_float2(s1, s2);
+        for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { s1[i] += v[j + i]; s2[i] = fmaf(v[j + i], v[j + i], s2[i]); }
+        }
+        unit_acc = make_float2((s1[0] + s1[1]) + (s1[2] + s1[3]), (s2[0] + s2[1]) + (s2[2] + s2[3]));
         if (HALF == 1 && row_ok && col0 < p.N) p.ln_stats[(size_t)row * (p.N >> 6) + (col0 >> 6)] = unit_acc;
       }
       uint4 w2[4];
@@ -472,15 +511,11 @@ __device__ __forceinline__ void epi_drain_tile_preloaded(uint32_t tmem_acc, cons
     uint32_t acc[32];
     tmem_ld32(tmem_acc + cc * 64, acc);
     tmem_wait_ld();
-#ifdef F5_EPI_PROBE
-    if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 3);
-#endif
+    F5_EPI_MARK(1, cc == 0, 3);    // first TMEM load landed
     if (colA < p.N)
       epi_apply<ACT, OUT_BF16, ROPE, 0>(acc, res[2 * cc], bias_s + cc * 64, gate_s + cc * 64, aux_s + cc * 64, cs, p, colA, row,
                                         b_idx, row_ok, row_valid, st, unit_acc);
-#ifdef F5_EPI_PROBE
-    if (cc == 0 && st.et == 0 && st.bar_id == 1) ts_mark(p, st.probe_cta, 4);
-#endif
+    F5_EPI_MARK(1, cc == 0, 4);    // chunk 0 complete
     tmem_ld32(tmem_acc + cc * 64 + 32, acc);
     tmem_wait_ld();
     if (colB < p.N)

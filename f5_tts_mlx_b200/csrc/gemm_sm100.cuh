@@ -47,6 +47,7 @@ struct GemmSmem {
   // epilogue store staging reuses the (idle) operand ring: fp32/bf16 chunks at [0, 64 KB) (32 KB per group), the
   // bf16 copy of the fused-LN producer mode at [64 KB, 96 KB) (16 KB per group, two alternating 8 KB buffers)
   static_assert(kStages * kStageBytes >= 98304, "operand ring too small for the epilogue staging");
+  static_assert(kTotal <= 232448, "single-CTA GEMM: shared memory over the 227 KB limit");
 };
 
 // Epilogue groups: 4 warps cover the 128 accumulator rows (TMEM lane quarter = warp % 4).  With 128-column
@@ -74,8 +75,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
   using S = GemmSmem<BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
+  // emits LDS / STS instead of generic LD / ST for everything derived from `smem`)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
@@ -298,6 +300,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
       stg.c2 = p.tiles_per_batch > 0 ? batch : 0;
       stg.bar_id = 1 + grp;
       stg.probe_cta = cta_lin;
+      stg.probe = p.ts != nullptr ? p.ts + (size_t)cta_lin * 10 : nullptr;
       stg.buf2 = smem + 65536 + grp * 16384;
       stg.buf2_par = 8192;
       stg.mu_r = ln_mu_r; stg.rstd = ln_rstd;
