@@ -13,11 +13,11 @@
 
 namespace f5 {
 
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8>
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8, bool RESID = true>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                        const GemmParams& p, dim3 grid, cudaStream_t stream) {
   using S = GemmSmem<BN, kStages>;
-  auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE, FP8>;
+  auto kern = gemm_bf16_tn_kernel<BN, kStages, ACT, OUT_BF16, ROPE, FP8, RESID>;
   static SmemAttrOnce once;  // per instantiation
   F5_CHECK_CUDA(ensure_dyn_smem(once, kern, S::kTotal));
   const double taps = p.conv_taps;
@@ -27,7 +27,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                stream);
   GemmParams q = p;
   q.prof = ps.slot;
-  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages>::kThreads), S::kTotal, stream, ta, tb, to, to2, q));
+  F5_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GemmEpi<BN, kStages, ROPE, RESID>::kThreads), S::kTotal, stream, ta, tb, to, to2, q));
   F5_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -37,6 +37,11 @@ static int dispatch_epi(int act, bool out_bf16, bool rope, const CUtensorMap& ta
                         const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2, const GemmParams& p,
                         dim3 grid, cudaStream_t stream) {
   const bool fp8 = p.ab8 || p.out_fp8 || p.out2_fp8;     // e4m3 features: separate instantiations (what the FP8 mode of the DiT uses)
+  // residual-free GELU epilogue of the two-CTAs-per-SM variant (FF1 at batch 1): two epilogue groups (gemm_sm100.cuh)
+  if (BN == 128 && kStages == 3 && p.resid == nullptr && act == ACT_GELU_TANH && out_bf16 && !rope) {
+    if (fp8) return launch_gemm<BN, kStages, ACT_GELU_TANH, true, false, true, false>(ta, tb, to, to2, p, grid, stream);
+    return launch_gemm<BN, kStages, ACT_GELU_TANH, true, false, false, false>(ta, tb, to, to2, p, grid, stream);
+  }
 #define F5_CASE8(A, O, R) \
   if (fp8 && act == A && out_bf16 == O && rope == R) return launch_gemm<BN, kStages, A, O, R, true>(ta, tb, to, to2, p, grid, stream);
   F5_CASE8(ACT_NONE, true, true)
@@ -210,13 +215,22 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a_in, void* stream_) {
   if (variant == 2) {
     int bn2 = a->tile_n;
     if (bn2 == 0) bn2 = (a->n % 256 == 0 || a->n >= 1024) ? 256 : 128;
-    // wide outputs on few row tiles (QKV at batch 1: 8 x 12 tiles of 256 columns on 74 SM pairs = two
-    // rounds, the second 30 % full): 192-column tiles give 8 x 16 smaller tiles
-    if (a->tile_n == 0 && bn2 == 256 && a->n % 192 == 0 && !a->out2_bf16) {
-      const int t256 = cdiv(a->m, 256) * cdiv(a->n, 256), t192 = cdiv(a->m, 256) * cdiv(a->n, 192);
-      const int pairs = sm_count() / 2;
-      const double c256 = (double)cdiv(t256, pairs) * 256, c192 = (double)cdiv(t192, pairs) * 192;
-      if (c192 < 0.85 * c256) bn2 = 192;   // only when it removes a mostly-empty round
+    // wide outputs on few row tiles (QKV at batch 1: 8 x 12 tiles of 256 columns on 74 SM pairs = two rounds, the
+    // second 30 % full): narrower tiles — 8 x 16 of 192 or 8 x 24 of 128 columns — only when they remove a mostly
+    // empty round; at equal cost the narrower tile wins (r02, same box: 128-wide 51.8 vs 192-wide 53.0 ms per step —
+    // its exposed last epilogue is two chunks per group instead of three, and three rounds overlap more of them)
+    if (a->tile_n == 0 && bn2 == 256 && !a->out2_bf16) {
+      const int pairs = sm_count() / 2, mt = cdiv(a->m, 256);
+      const double c256 = (double)cdiv(mt * cdiv(a->n, 256), pairs) * 256;
+      double best = c256;
+      if (a->n % 192 == 0) {
+        const double c192 = (double)cdiv(mt * cdiv(a->n, 192), pairs) * 192;
+        if (c192 < 0.85 * c256) { bn2 = 192; best = c192; }
+      }
+      if (a->n % 128 == 0) {
+        const double c128 = (double)cdiv(mt * cdiv(a->n, 128), pairs) * 128;
+        if (c128 < 0.85 * c256 && c128 <= best) bn2 = 128;
+      }
     }
     F5_REQUIRE(bn2 == 128 || bn2 == 192 || bn2 == 256, "f5_gemm_bf16: CTA-pair tile_n must be 128, 192 or 256");
     GemmParams p2;

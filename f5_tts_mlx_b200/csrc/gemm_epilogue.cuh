@@ -371,23 +371,24 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
-  if (p.gate != nullptr) {
-    if (p.gate_ld == 0) {
+  if (p.gate != nullptr && p.gate_ld == 0) {     // residual + gate * v as one FMA per element
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 gg = *reinterpret_cast<const float4*>(gate_s + j);
-        v[j] *= gg.x; v[j + 1] *= gg.y; v[j + 2] *= gg.z; v[j + 3] *= gg.w;
-      }
-    } else {   // per-utterance gates (not used by sample(): all utterances share the time value)
+    for (int j = 0; j < 8; ++j) {
+      const float4 gg = *reinterpret_cast<const float4*>(gate_s + 4 * j);
+      v[4 * j] = fmaf(v[4 * j], gg.x, res[j].x); v[4 * j + 1] = fmaf(v[4 * j + 1], gg.y, res[j].y);
+      v[4 * j + 2] = fmaf(v[4 * j + 2], gg.z, res[j].z); v[4 * j + 3] = fmaf(v[4 * j + 3], gg.w, res[j].w);
+    }
+  } else {
+    if (p.gate != nullptr) {   // per-utterance gates (not used by sample(): all utterances share the time value)
       const float* g = p.gate + (size_t)b_idx * p.gate_ld + col0;
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) v[j] *= g[j];
     }
-  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+    }
   }
   if constexpr (!OUT_BF16) {
     if (p.out2 != nullptr) {

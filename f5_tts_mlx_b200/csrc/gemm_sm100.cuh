@@ -55,9 +55,16 @@ struct GemmSmem {
 // B=1 GEMMs the epilogue is a serial tail behind the main loop (in-situ timelines: 3.0-4.2 us of a 10-17 us
 // kernel with one group), and its cost is latency (TMEM load -> math -> staged store), not bandwidth.
 // (Only for the one-CTA-per-SM variant: with two co-resident CTAs 320 threads would leave 96 registers.)
-template <int BN, int kStages>
+// (r02: F5_TWO_GROUPS_2CTA=1 gives the two-CTAs-per-SM variant a second group too when its epilogue holds neither a
+// RoPE table nor residual tiles — FF1 at batch 1; 2 x 320 threads leave 96 registers, which that epilogue fits without
+// spilling.  Measured SLOWER on the same box, 53.0 vs 52.55 ms per step: four epilogue groups per SM compete with the
+// co-resident CTA's main loop.  Off.)
+#ifndef F5_TWO_GROUPS_2CTA
+#define F5_TWO_GROUPS_2CTA 0
+#endif
+template <int BN, int kStages, bool ROPE = false, bool RESID = true>
 struct GemmEpi {
-  static constexpr int kGroups = (BN >= 128 && kStages > 4) ? 2 : 1;
+  static constexpr int kGroups = (BN >= 128 && (kStages > 4 || (F5_TWO_GROUPS_2CTA && !ROPE && !RESID))) ? 2 : 1;
   static constexpr int kThreads = 64 + 128 * kGroups;
   static constexpr int kCols = BN / kGroups;          // columns per group
 };
@@ -65,13 +72,15 @@ struct GemmEpi {
 // FP8 = false instantiations have every e4m3 feature (ab8 / out_fp8 / out2_fp8 / acc_scale) folded away at compile
 // time: the prologue, the issue loop and the epilogue are sensitive to every extra instruction (r02: carrying the
 // run-time flags cost the bf16 path 1-3 % of the step), so only the FP8 mode pays for the FP8 mode.
-template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8 = false>
-__global__ void __launch_bounds__(GemmEpi<BN, kStages>::kThreads, (kStages > 4) ? 1 : 2)
+// RESID = false instantiations (no residual input) drop the residual tiles from the epilogue's registers.
+template <int BN, int kStages, int ACT, bool OUT_BF16, bool ROPE, bool FP8 = false, bool RESID = true>
+__global__ void __launch_bounds__(GemmEpi<BN, kStages, ROPE, RESID>::kThreads, (kStages > 4) ? 1 : 2)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                     const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                     const __grid_constant__ CUtensorMap tma_out2, const GemmParams p_arg) {
   GemmParams p = p_arg;
   if constexpr (!FP8) { p.ab8 = 0; p.out_fp8 = 0; p.out2_fp8 = 0; p.acc_scale = 1.f; }
+  if constexpr (!RESID) p.resid = nullptr;
   using S = GemmSmem<BN, kStages>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles must sit on 1024-byte boundaries
@@ -237,7 +246,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     else mma_loop(std::false_type{});
   } else {
     // ===================== epilogue =====================
-    using E = GemmEpi<BN, kStages>;
+    using E = GemmEpi<BN, kStages, ROPE, RESID>;
     constexpr int BNG = E::kCols;
     const int grp = (warp - 2) >> 2;       // 0: columns [0, BNG), 1: [BNG, BN)
     const int lg = warp & 3;               // TMEM lane group this warp may access
@@ -317,7 +326,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     if (et == 0) tma_store_wait_read<0>();   // the staging buffers must outlive the TMA unit's reads; grid completion
                                              // makes the global writes visible to the dependent kernel
     tc_fence_before();
-    if (warp == 2 + 4 * (GemmEpi<BN, kStages>::kGroups - 1) && lane == 0) ts_mark(p, cta_lin, 8);
+    if (warp == 2 + 4 * (GemmEpi<BN, kStages, ROPE, RESID>::kGroups - 1) && lane == 0) ts_mark(p, cta_lin, 8);
   }
 
   __syncthreads();
