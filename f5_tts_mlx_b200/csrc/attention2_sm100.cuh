@@ -125,7 +125,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
-  if (threadIdx.x == 0) prof_stamp_begin(p.prof);
+  if (threadIdx.x == 128) prof_stamp_begin(p.prof);   // a softmax thread, not the producer
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");

@@ -227,7 +227,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   }
   pdl_wait();
-  if (threadIdx.x == 0) { ts_mark(p, blockIdx.x, 2); prof_stamp_begin(p.prof); }
+  if (threadIdx.x == 128) { ts_mark(p, blockIdx.x, 2); prof_stamp_begin(p.prof); }   // an epilogue thread, not the producer
 
   // register hand-over (384 threads cap every thread at 168): warps 0-3 need few, the epilogue warps hold a
   // row's RoPE table, residual and accumulator chunk.  128 x 40 + 256 x 232 = 64 512 = exactly the 384 x 168 registers

@@ -367,9 +367,11 @@ __device__ __forceinline__ void epi_apply(const uint32_t (&acc)[32], const float
       for (int j = 0; j < 32; ++j) v[j] *= p.q_scale;
     }
   }
-  if (!row_valid) {
+  if (p.row_len != nullptr) {     // uniform: GEMMs without a row mask skip the 32 predicated moves
+    if (!row_valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
   }
   if (p.gate != nullptr && p.gate_ld == 0) {     // residual + gate * v as one FMA per element
 #pragma unroll

@@ -145,7 +145,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   }
   pdl_wait();   // predecessor's outputs (our A operand / residual) are complete and visible
-  if (threadIdx.x == 0) { ts_mark(p, cta_lin, 2); prof_stamp_begin(p.prof); }
+  if (threadIdx.x == 64) { ts_mark(p, cta_lin, 2); prof_stamp_begin(p.prof); }   // an epilogue thread: the producer goes straight to its first load
 
   if (warp == 0) {
     // ===================== TMA producer =====================
